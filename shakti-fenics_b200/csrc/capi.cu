@@ -1,0 +1,998 @@
+// C ABI of the B200-native SHAKTI solver (include/shakti_b200.h): the model object, the
+// Newton loop, the time step and the parity hooks.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+
+#include "amg.h"
+#include "comm.h"
+#include "device.h"
+#include "krylov.h"
+
+namespace shakti {
+
+static thread_local std::string t_last_error;
+void set_last_error(const std::string& msg) { t_last_error = msg; }
+
+// default degree-7 table: collapsed Gauss-Jacobi 4x4 (stand-in for Basix' default; see
+// shakti_b200/quadrature.py which generates these digits and tests/test_quadrature.py)
+static void default_k_rule(std::vector<double>& pts, std::vector<double>& wts);
+// Radon's 7-point degree-5 rule
+static void radon7(std::vector<double>& pts, std::vector<double>& wts) {
+  const double s15 = std::sqrt(15.0);
+  const double a[2] = {(6.0 - s15) / 21.0, (6.0 + s15) / 21.0};
+  const double w[2] = {(155.0 - s15) / 1200.0, (155.0 + s15) / 1200.0};
+  pts = {1.0 / 3.0, 1.0 / 3.0};
+  wts = {0.5 * 9.0 / 40.0};
+  for (int k = 0; k < 2; ++k) {
+    const double c = 1.0 - 2.0 * a[k];
+    const double l[3][3] = {{c, a[k], a[k]}, {a[k], c, a[k]}, {a[k], a[k], c}};
+    for (int i = 0; i < 3; ++i) {
+      pts.push_back(l[i][1]);
+      pts.push_back(l[i][2]);
+      wts.push_back(0.5 * w[k]);
+    }
+  }
+}
+
+}  // namespace shakti
+
+using namespace shakti;
+
+struct shakti_model {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  shakti_params prm;
+  DevParams dprm;
+  shakti_options opt;
+  HostMesh hm;
+  std::vector<int32_t> cells_g;   // caller cells (parity hooks, Dirichlet location)
+  std::unique_ptr<HostCsr> csr_g; // caller CSR pattern, built lazily
+  // quadrature
+  std::vector<double> kq_pts, kq_wts;
+  // device mesh
+  DevBuf<double> x, y;
+  DevBuf<int32_t> c0, c1, c2, slot, diag_pos, win, l2g;
+  // vertex fields (n_local)
+  DevBuf<double> z_b, z_s, h0, G, inputs, storage, b, b2, N, N_n, qx, qy, melt, melt2, F, dx, rhs, dinv;
+  DevBuf<double> kbar;
+  DevBuf<uint8_t> isbc;
+  DevBuf<double> stage;   // nv_g doubles: caller-numbered staging for set/get
+  DevBuf<double> stage2;  // 2 nv_g (interleaved flux)
+  DevBuf<double> scal;    // small device scalars
+  double* host_scal = nullptr;  // pinned
+  double N_bdry = 0.0;
+  int64_t n_bc = 0;
+  bool h0_dirty = true;
+  DevSell J;
+  bool J_valid = false;
+  HaloPlan halo;
+  Gmres gmres;
+  BiCgStab bicg;
+  bool bicg_init = false;
+  Reducer red;
+  std::unique_ptr<Amg> amg;
+  bool amg_setup_done = false;
+  int64_t solves_since_refresh = 0;
+  // Newton state
+  double residual0 = 0.0;  // DOLFINx NewtonSolver::_residual0 (kept across solves)
+  shakti_stats st{};
+  int64_t launches_at_create = 0;
+
+  FieldPtrs fields() const {
+    FieldPtrs f;
+    f.x = x.p; f.y = y.p; f.h0 = h0.p; f.N = N.p; f.N_n = N_n.p; f.b = b.p; f.qx = qx.p; f.qy = qy.p;
+    f.G = G.p; f.melt = melt.p; f.storage = storage.p; f.inputs = inputs.p; f.isbc = isbc.p;
+    return f;
+  }
+};
+
+namespace shakti {
+
+static void use_device(shakti_model* m) { SHAKTI_CUDA(cudaSetDevice(m->device)); }
+
+static void refresh_h0(shakti_model* m) {
+  if (!m->h0_dirty) return;
+  launch_head0(m->hm.n_local, m->z_b.p, m->z_s.p, m->prm.rho_i / m->prm.rho_w, m->h0.p, m->stream);
+  m->h0_dirty = false;
+}
+
+static double* field_ptr(shakti_model* m, int f) {
+  switch (f) {
+    case SHAKTI_F_Z_B: return m->z_b.p;
+    case SHAKTI_F_Z_S: return m->z_s.p;
+    case SHAKTI_F_G: return m->G.p;
+    case SHAKTI_F_INPUTS: return m->inputs.p;
+    case SHAKTI_F_STORAGE: return m->storage.p;
+    case SHAKTI_F_B: return m->b.p;
+    case SHAKTI_F_N: return m->N.p;
+    case SHAKTI_F_N_N: return m->N_n.p;
+    case SHAKTI_F_QX: return m->qx.p;
+    case SHAKTI_F_QY: return m->qy.p;
+    case SHAKTI_F_MELT_N: return m->melt.p;
+    case SHAKTI_F_RESIDUAL: return m->F.p;
+    default: throw Error(SHAKTI_ERR_INVALID, "unknown field id");
+  }
+}
+
+// caller-numbered device array (nv_g) -> local field (n_local, ghosts included)
+static void scatter_in(shakti_model* m, const double* src_dev, double* field) {
+  launch_gather(m->hm.n_local, m->l2g.p, src_dev, field, m->stream);
+}
+// local field (owned part) -> caller-numbered device array; entries of other ranks are 0
+static void gather_out(shakti_model* m, const double* field, double* dst_dev) {
+  if (comm().active()) SHAKTI_CUDA(cudaMemsetAsync(dst_dev, 0, sizeof(double) * m->hm.nv_g, m->stream));
+  launch_scatter(m->hm.n_owned, m->l2g.p, field, dst_dev, m->stream);
+}
+
+static void set_field(shakti_model* m, int f, const double* src, int is_device) {
+  SHAKTI_REQUIRE(f >= 0 && f < SHAKTI_F_COUNT && f != SHAKTI_F_RESIDUAL, "field is not writable");
+  SHAKTI_REQUIRE(src != nullptr, "null source");
+  const double* s = src;
+  if (!is_device) {
+    SHAKTI_CUDA(cudaMemcpyAsync(m->stage.p, src, sizeof(double) * m->hm.nv_g, cudaMemcpyHostToDevice, m->stream));
+    s = m->stage.p;
+  }
+  scatter_in(m, s, field_ptr(m, f));
+  if (f == SHAKTI_F_Z_B || f == SHAKTI_F_Z_S) m->h0_dirty = true;
+  if (!is_device) SHAKTI_CUDA(cudaStreamSynchronize(m->stream));
+}
+
+static void get_field(shakti_model* m, int f, double* dst, int is_device) {
+  SHAKTI_REQUIRE(f >= 0 && f < SHAKTI_F_COUNT, "unknown field id");
+  SHAKTI_REQUIRE(dst != nullptr, "null destination");
+  if (is_device) {
+    gather_out(m, field_ptr(m, f), dst);
+  } else {
+    gather_out(m, field_ptr(m, f), m->stage.p);
+    SHAKTI_CUDA(cudaMemcpyAsync(dst, m->stage.p, sizeof(double) * m->hm.nv_g, cudaMemcpyDeviceToHost, m->stream));
+    SHAKTI_CUDA(cudaStreamSynchronize(m->stream));
+  }
+}
+
+static void allreduce(shakti_model* m, double* dev, int count) { comm_allreduce_sum(dev, count, m->stream); }
+
+static double norm2(shakti_model* m, const double* v) {
+  launch_multi_dot(m->red, m->hm.n_owned, 1, v, m->hm.n_owned, v, m->scal.p, m->stream);
+  allreduce(m, m->scal.p, 1);
+  SHAKTI_CUDA(cudaMemcpyAsync(m->host_scal, m->scal.p, sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  SHAKTI_CUDA(cudaStreamSynchronize(m->stream));
+  return std::sqrt(std::max(m->host_scal[0], 0.0));
+}
+
+static void compute_kbar(shakti_model* m) {
+  launch_kbar(m->hm.ne, m->c0.p, m->c1.p, m->c2.p, m->x.p, m->y.p, m->b.p, m->qx.p, m->qy.p, m->kbar.p,
+              m->dprm, m->stream);
+}
+
+// residual (+ Jacobian) at the current state; Kbar must be current
+static void assemble(shakti_model* m, double dt, int want_J) {
+  refresh_h0(m);
+  const int32_t no = m->hm.n_owned;
+  SHAKTI_CUDA(cudaMemsetAsync(m->F.p, 0, sizeof(double) * no, m->stream));
+  if (want_J) SHAKTI_CUDA(cudaMemsetAsync(m->J.val.p, 0, sizeof(double) * m->J.padded, m->stream));
+  launch_assemble_atomic(m->hm.ne, no, m->c0.p, m->c1.p, m->c2.p, m->slot.p, m->fields(), m->kbar.p, dt,
+                         m->N_bdry, m->F.p, m->J.val.p, want_J, m->dprm, m->stream);
+  if (m->n_bc) launch_apply_bc(no, m->isbc.p, m->N.p, m->N_bdry, m->diag_pos.p, m->F.p, m->J.val.p, want_J, m->stream);
+  if (want_J) m->J_valid = true;
+}
+
+static void ensure_amg(shakti_model* m) {
+  if (m->amg_setup_done) return;
+  AmgOptions ao;
+  ao.max_levels = m->opt.amg_max_levels;
+  ao.coarse_size = m->opt.amg_coarse_size;
+  ao.presmooth = m->opt.amg_presmooth;
+  ao.postsmooth = m->opt.amg_postsmooth;
+  ao.smoother_omega = m->opt.amg_smoother_omega;
+  ao.prolong_omega = m->opt.amg_prolong_omega;
+  std::vector<uint8_t> excl = m->isbc.download(m->stream);
+  excl.resize(m->hm.n_owned);
+  m->amg.reset(new Amg());
+  m->amg->setup(m->hm.A, m->hm.S, excl, ao, m->sm_count, m->stream);
+  m->amg_setup_done = true;
+  m->solves_since_refresh = 0;
+}
+
+// Solve J dx = rhs (rhs, dx owned-length device vectors) with the configured method.
+static KrylovResult linear_solve(shakti_model* m, const double* rhs, double* dx) {
+  SHAKTI_REQUIRE(m->J_valid, "no assembled Jacobian");
+  const int32_t no = m->hm.n_owned;
+  SellView Jv = view(m->J);
+  ApplyFn A = [m, Jv](double* xl, double* y) {
+    m->halo.exchange(xl, m->stream);
+    launch_spmv(Jv, xl, y, m->stream);
+  };
+  PrecFn M;
+  if (m->opt.precond == SHAKTI_PC_JACOBI) {
+    launch_extract_dinv(no, m->diag_pos.p, m->J.val.p, m->dinv.p, m->stream);
+    M = [m, no](const double* r, double* z) { launch_pointwise_mul(no, m->dinv.p, r, 1.0, z, m->stream); };
+  } else if (m->opt.precond == SHAKTI_PC_AMG) {
+    ensure_amg(m);
+    const int every = std::max(1, m->opt.amg_refresh_every);
+    if (!m->amg->ready() || (m->solves_since_refresh % every) == 0) {
+      m->amg->refresh(m->J, m->diag_pos.p);
+      m->st.amg_refreshes++;
+    }
+    m->solves_since_refresh++;
+    M = [m](const double* r, double* z) { m->amg->apply(m->J, r, z); };
+  } else {
+    M = [m, no](const double* r, double* z) {
+      SHAKTI_CUDA(cudaMemcpyAsync(z, r, sizeof(double) * no, cudaMemcpyDeviceToDevice, m->stream));
+    };
+  }
+  AllReduceFn ar = [m](double* d, int c) { allreduce(m, d, c); };
+  KrylovResult r;
+  if (m->opt.linear_solver == SHAKTI_KSP_BICGSTAB) {
+    if (!m->bicg_init) { m->bicg.init(no, m->hm.n_local, m->sm_count, m->stream); m->bicg_init = true; }
+    r = m->bicg.solve(A, M, ar, rhs, dx, m->opt.linear_rtol, m->opt.linear_atol, m->opt.linear_max_it);
+  } else {
+    r = m->gmres.solve(A, M, ar, rhs, dx, m->opt.linear_rtol, m->opt.linear_atol, m->opt.linear_max_it);
+  }
+  m->st.linear_its += r.iterations;
+  m->st.last_linear_relres = r.relres;
+  return r;
+}
+
+// dx[bc] = F[bc]   (identity rows of J)
+__global__ void fix_bc_dx_kernel(int32_t n, const uint8_t* __restrict__ isbc, const double* __restrict__ F,
+                                 double* __restrict__ dx) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && isbc[i]) dx[i] = F[i];
+}
+
+// DOLFINx NewtonSolver::solve (criterion "residual", relaxation 1, LU replaced by Krylov)
+static void newton_solve(shakti_model* m, double dt, int32_t* niter, int32_t* converged) {
+  const int32_t no = m->hm.n_owned;
+  compute_kbar(m);
+  assemble(m, dt, 1);
+  double r = norm2(m, m->F.p);
+  const double r_init = r;
+  auto check = [&](double res) {
+    double rel;
+    if (m->opt.newton_r0 == SHAKTI_R0_DOLFINX) rel = m->residual0 > 0 ? res / m->residual0 : INFINITY;
+    else rel = r_init > 0 ? res / r_init : 0.0;
+    return rel < m->opt.newton_rtol || res < m->opt.newton_atol;
+  };
+  bool conv = check(r);
+  int it = 0;
+  while (!conv && it < m->opt.newton_max_it) {
+    // Dirichlet rows are identity rows and their columns are zero: solve the interior system
+    launch_xmy_masked(no, m->F.p, m->isbc.p, m->rhs.p, m->stream);
+    KrylovResult kr = linear_solve(m, m->rhs.p, m->dx.p);
+    if (!kr.converged)
+      throw Error(SHAKTI_ERR_LINEAR, "Krylov solve did not reach its tolerance (relres " +
+                                         std::to_string(kr.relres) + " after " + std::to_string(kr.iterations) + " its)");
+    if (m->n_bc) SHAKTI_LAUNCH(fix_bc_dx_kernel, div_up(no, 256), 256, 0, m->stream, no, m->isbc.p, m->F.p, m->dx.p);
+    launch_axpy(no, -1.0, m->dx.p, m->N.p, m->stream);   // x <- x - dx
+    m->halo.exchange(m->N.p, m->stream);
+    ++it;
+    if (it == 1 && m->opt.newton_r0 == SHAKTI_R0_DOLFINX) m->residual0 = norm2(m, m->dx.p);
+    assemble(m, dt, 1);
+    r = norm2(m, m->F.p);
+    conv = check(r);
+  }
+  m->st.newton_its += it;
+  m->st.last_residual = r;
+  m->st.last_residual0 = m->opt.newton_r0 == SHAKTI_R0_DOLFINX ? m->residual0 : r_init;
+  *niter = it;
+  *converged = conv ? 1 : 0;
+  if (!conv) throw Error(SHAKTI_ERR_NOT_CONVERGED, "Newton solver did not converge");
+}
+
+static void update_q(shakti_model* m) {
+  refresh_h0(m);
+  launch_update_q(m->hm.n_owned, m->win.p, m->x.p, m->y.p, m->h0.p, m->N.p, m->b.p, m->qx.p, m->qy.p, m->dprm, m->stream);
+}
+static void update_melt(shakti_model* m) {
+  refresh_h0(m);
+  launch_update_melt(m->hm.n_owned, m->win.p, m->x.p, m->y.p, m->h0.p, m->N.p, m->b.p, m->qx.p, m->qy.p, m->G.p,
+                     m->melt.p, m->melt2.p, m->dprm, m->stream);
+  std::swap(m->melt.p, m->melt2.p);
+  m->halo.exchange(m->melt.p, m->stream);
+}
+static void update_b(shakti_model* m, double dt) {
+  refresh_h0(m);
+  launch_update_b(m->hm.n_owned, m->win.p, m->x.p, m->y.p, m->h0.p, m->N.p, m->b.p, m->qx.p, m->qy.p, m->G.p,
+                  m->melt.p, m->b2.p, dt, m->opt.b_min, m->dprm, m->stream);
+  std::swap(m->b.p, m->b2.p);
+  m->halo.exchange(m->b.p, m->stream);
+  m->halo.exchange(m->qx.p, m->stream);
+  m->halo.exchange(m->qy.p, m->stream);
+}
+static void copy_N(shakti_model* m) {
+  SHAKTI_CUDA(cudaMemcpyAsync(m->N_n.p, m->N.p, sizeof(double) * m->hm.n_local, cudaMemcpyDeviceToDevice, m->stream));
+}
+
+static void step(shakti_model* m, double dt, int32_t* niter, int32_t* converged) {
+  SHAKTI_REQUIRE(dt > 0, "dt must be positive");
+  int32_t it = 0, cv = 0;
+  newton_solve(m, dt, &it, &cv);
+  update_q(m);
+  update_melt(m);
+  update_b(m, dt);
+  copy_N(m);
+  m->st.steps++;
+  if (niter) *niter = it;
+  if (converged) *converged = cv;
+}
+
+static void set_dirichlet(shakti_model* m, const int32_t* dofs, int64_t n, double value) {
+  std::vector<uint8_t> flag(m->hm.n_local, 0);
+  for (int64_t i = 0; i < n; ++i) {
+    SHAKTI_REQUIRE(dofs[i] >= 0 && dofs[i] < m->hm.nv_g, "Dirichlet dof out of range");
+    const int32_t l = m->hm.g2l[dofs[i]];
+    if (l >= 0) flag[l] = 1;
+  }
+  m->isbc.upload(flag);
+  m->N_bdry = value;
+  m->n_bc = n;   // global count: >0 on every rank
+  m->amg_setup_done = false;  // excluded rows changed
+  m->amg.reset();
+}
+
+static HostCsr& caller_pattern(shakti_model* m) {
+  if (!m->csr_g) m->csr_g.reset(new HostCsr(caller_csr(m->hm.nv_g, m->hm.ne_g, m->cells_g.data())));
+  return *m->csr_g;
+}
+
+static void create(int64_t nv, int64_t ne, const double* xy, const int32_t* cells, const shakti_params* params,
+                   const shakti_options* opt, int device, shakti_model** out) {
+  SHAKTI_REQUIRE(out && xy && cells, "null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    throw Error(SHAKTI_ERR_NO_DEVICE, "no CUDA device: the SHAKTI B200 path has no CPU fallback");
+  }
+  std::unique_ptr<shakti_model> m(new shakti_model());
+  if (device < 0) SHAKTI_CUDA(cudaGetDevice(&device));
+  m->device = device;
+  SHAKTI_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  SHAKTI_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    throw Error(SHAKTI_ERR_NO_DEVICE, std::string("device '") + prop.name + "' is not sm_100 class; this library is built for sm_100a only");
+  m->sm_count = prop.multiProcessorCount;
+  SHAKTI_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  if (params) m->prm = *params; else shakti_default_params(&m->prm);
+  if (opt) m->opt = *opt; else shakti_default_options(&m->opt);
+  m->dprm = make_dev_params(m->prm);
+  m->launches_at_create = g_kernel_launches;
+  m->cells_g.assign(cells, cells + 3 * ne);
+  build_host_mesh(nv, ne, xy, cells, comm().rank, comm().nranks, m->opt.reorder, m->hm);
+  HostMesh& hm = m->hm;
+  // device mesh
+  m->x.upload(hm.x);
+  m->y.upload(hm.y);
+  {
+    std::vector<int32_t> a(hm.ne), b(hm.ne), c(hm.ne);
+    for (int32_t e = 0; e < hm.ne; ++e) { a[e] = hm.cells[3 * (size_t)e]; b[e] = hm.cells[3 * (size_t)e + 1]; c[e] = hm.cells[3 * (size_t)e + 2]; }
+    m->c0.upload(a); m->c1.upload(b); m->c2.upload(c);
+  }
+  m->slot.upload(hm.slot);
+  m->diag_pos.upload(hm.diag_pos);
+  m->win.upload(hm.win);
+  m->l2g.upload(hm.l2g);
+  const size_t nl = std::max<int32_t>(hm.n_local, 1);
+  for (DevBuf<double>* f : {&m->z_b, &m->z_s, &m->h0, &m->G, &m->inputs, &m->storage, &m->b, &m->b2, &m->N, &m->N_n,
+                            &m->qx, &m->qy, &m->melt, &m->melt2, &m->F, &m->dx, &m->rhs, &m->dinv})
+    f->alloc_zero(nl, m->stream);
+  m->kbar.alloc_zero(std::max<int32_t>(hm.ne, 1), m->stream);
+  m->isbc.alloc_zero(nl, m->stream);
+  m->stage.alloc((size_t)nv);
+  m->scal.alloc_zero(16, m->stream);
+  SHAKTI_CUDA(cudaMallocHost(&m->host_scal, 16 * sizeof(double)));
+  m->J.upload_pattern(hm.S, hm.A.nnz());
+  m->halo.build(hm.nbrs);
+  m->red.init(m->sm_count);
+  m->gmres.init(hm.n_owned, hm.n_local, std::max(2, m->opt.gmres_restart), m->sm_count, m->stream);
+  // quadrature tables
+  default_k_rule(m->kq_pts, m->kq_wts);
+  upload_k_rule((int)m->kq_wts.size(), m->kq_pts.data(), m->kq_wts.data(), m->stream);
+  {
+    std::vector<double> p, w;
+    if (m->dprm.n_is_3) radon7(p, w); else { p = m->kq_pts; w = m->kq_wts; }
+    upload_reaction_rule((int)w.size(), p.data(), w.data(), m->stream);
+  }
+  // stats
+  m->st.n_vert = nv; m->st.n_cell = ne;
+  m->st.n_owned = hm.n_owned; m->st.n_local = hm.n_local; m->st.n_cell_local = hm.ne; m->st.nnz_local = hm.A.nnz();
+  m->st.nnz = comm().active() ? -1 : hm.A.nnz();
+  SHAKTI_CUDA(cudaStreamSynchronize(m->stream));
+  *out = m.release();
+}
+
+static void destroy(shakti_model* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  if (m->stream) cudaStreamSynchronize(m->stream);
+  // swap-safe: DevBuf destructors free whatever pointer they currently hold
+  if (m->host_scal) cudaFreeHost(m->host_scal);
+  cudaStream_t s = m->stream;
+  delete m;
+  if (s) cudaStreamDestroy(s);
+}
+
+// n-point Gauss rule for the weight (1-x)^alpha (1+x)^beta on [-1,1] by Golub-Welsch: nodes are
+// the eigenvalues of the Jacobi matrix of the monic recurrence, weights mu0 * (first eigenvector
+// component)^2.  The small symmetric eigenproblem is solved with cyclic Jacobi rotations.
+static void gauss_jacobi(int n, long double alpha, long double beta, std::vector<long double>& x,
+                         std::vector<long double>& w) {
+  std::vector<long double> T((size_t)n * n, 0.0L), Q((size_t)n * n, 0.0L);
+  const long double ab = alpha + beta;
+  for (int k = 0; k < n; ++k) {
+    long double a;
+    if (k == 0) a = (beta - alpha) / (ab + 2.0L);
+    else a = (beta * beta - alpha * alpha) / ((2.0L * k + ab) * (2.0L * k + ab + 2.0L));
+    T[(size_t)k * n + k] = a;
+    if (k >= 1) {
+      long double b;
+      if (k == 1) b = 4.0L * (1.0L + alpha) * (1.0L + beta) / ((2.0L + ab) * (2.0L + ab) * (3.0L + ab));
+      else {
+        const long double t = 2.0L * k + ab;
+        b = 4.0L * k * (k + alpha) * (k + beta) * (k + ab) / (t * t * (t + 1.0L) * (t - 1.0L));
+      }
+      T[(size_t)k * n + k - 1] = T[(size_t)(k - 1) * n + k] = std::sqrt(b);
+    }
+    Q[(size_t)k * n + k] = 1.0L;
+  }
+  for (int sweep = 0; sweep < 100; ++sweep) {
+    long double off = 0.0L;
+    for (int p = 0; p < n; ++p)
+      for (int q = p + 1; q < n; ++q) off += T[(size_t)p * n + q] * T[(size_t)p * n + q];
+    if (off < 1e-40L) break;
+    for (int p = 0; p < n; ++p)
+      for (int q = p + 1; q < n; ++q) {
+        const long double apq = T[(size_t)p * n + q];
+        if (apq == 0.0L) continue;
+        const long double theta = (T[(size_t)q * n + q] - T[(size_t)p * n + p]) / (2.0L * apq);
+        const long double t = (theta >= 0 ? 1.0L : -1.0L) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0L));
+        const long double c = 1.0L / std::sqrt(t * t + 1.0L), sn = t * c;
+        for (int k = 0; k < n; ++k) {  // columns p,q of T
+          const long double kp = T[(size_t)k * n + p], kq = T[(size_t)k * n + q];
+          T[(size_t)k * n + p] = c * kp - sn * kq;
+          T[(size_t)k * n + q] = sn * kp + c * kq;
+        }
+        for (int k = 0; k < n; ++k) {  // rows p,q of T
+          const long double pk = T[(size_t)p * n + k], qk = T[(size_t)q * n + k];
+          T[(size_t)p * n + k] = c * pk - sn * qk;
+          T[(size_t)q * n + k] = sn * pk + c * qk;
+        }
+        for (int k = 0; k < n; ++k) {  // accumulate eigenvectors (columns of Q)
+          const long double kp = Q[(size_t)k * n + p], kq = Q[(size_t)k * n + q];
+          Q[(size_t)k * n + p] = c * kp - sn * kq;
+          Q[(size_t)k * n + q] = sn * kp + c * kq;
+        }
+      }
+  }
+  const long double mu0 = std::pow(2.0L, ab + 1.0L) * std::tgamma(alpha + 1.0L) * std::tgamma(beta + 1.0L) /
+                          std::tgamma(ab + 2.0L);
+  std::vector<int> order(n);
+  for (int i = 0; i < n; ++i) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return T[(size_t)a * n + a] < T[(size_t)b * n + b]; });
+  x.resize(n);
+  w.resize(n);
+  for (int i = 0; i < n; ++i) {
+    const int j = order[i];
+    x[i] = T[(size_t)j * n + j];
+    w[i] = mu0 * Q[j] * Q[j];  // first row of Q, column j
+  }
+}
+
+// collapsed (Duffy) Gauss-Jacobi rule of degree 7: 4 x 4 points, weights sum to 1/2
+static void default_k_rule(std::vector<double>& pts, std::vector<double>& wts) {
+  std::vector<long double> xu, wu, xv, wv;
+  gauss_jacobi(4, 1.0L, 0.0L, xu, wu);
+  gauss_jacobi(4, 0.0L, 0.0L, xv, wv);
+  pts.clear();
+  wts.clear();
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      const long double u = 0.5L * (1.0L + xu[i]), v = 0.5L * (1.0L + xv[j]);
+      pts.push_back((double)u);
+      pts.push_back((double)(v * (1.0L - u)));
+      wts.push_back((double)(0.25L * wu[i] * 0.5L * wv[j]));
+    }
+}
+
+}  // namespace shakti
+
+// ====================================================================== extern "C"
+#define SHAKTI_TRY try {
+#define SHAKTI_CATCH                                      \
+  }                                                       \
+  catch (const shakti::Error& e) {                        \
+    shakti::set_last_error(e.what());                     \
+    return e.code;                                        \
+  }                                                       \
+  catch (const std::exception& e) {                       \
+    shakti::set_last_error(e.what());                     \
+    return SHAKTI_ERR_INVALID;                            \
+  }                                                       \
+  return SHAKTI_OK;
+
+extern "C" {
+
+const char* shakti_last_error(void) { return shakti::t_last_error.c_str(); }
+const char* shakti_version(void) { return "shakti_b200 0.1 (sm_100a)"; }
+
+int shakti_default_params(shakti_params* p) {
+  if (!p) return SHAKTI_ERR_INVALID;
+  p->g = 9.81; p->rho_i = 917; p->rho_w = 1000; p->nu = 1.787e-6; p->Lh = 3.34e5; p->omega = 1e-3; p->n = 3; p->A = 2.24e-24;
+  return SHAKTI_OK;
+}
+
+int shakti_default_options(shakti_options* o) {
+  if (!o) return SHAKTI_ERR_INVALID;
+  o->newton_rtol = 1e-9; o->newton_atol = 1e-10; o->newton_max_it = 50; o->newton_r0 = SHAKTI_R0_DOLFINX;
+  o->linear_solver = SHAKTI_KSP_GMRES; o->precond = SHAKTI_PC_AMG;
+  o->linear_rtol = 1e-12; o->linear_atol = 0.0; o->linear_max_it = 2000; o->gmres_restart = 40;
+  o->amg_refresh_every = 1; o->amg_max_levels = 12; o->amg_coarse_size = 128; o->amg_presmooth = 1; o->amg_postsmooth = 1;
+  o->amg_smoother_omega = 0.67; o->amg_prolong_omega = 0.67;
+  o->b_min = 1.0e-5; o->assembly_kernel = 1; o->reorder = 1;
+  return SHAKTI_OK;
+}
+
+int shakti_create(int64_t n_vert, int64_t n_cell, const double* xy, const int32_t* cells, const shakti_params* params,
+                  const shakti_options* opt, int device, shakti_model** out) {
+  SHAKTI_TRY
+  shakti::create(n_vert, n_cell, xy, cells, params, opt, device, out);
+  SHAKTI_CATCH
+}
+
+int shakti_destroy(shakti_model* m) {
+  SHAKTI_TRY
+  shakti::destroy(m);
+  SHAKTI_CATCH
+}
+
+int shakti_set_field(shakti_model* m, int field, const double* src, int is_device) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(m, "null model");
+  use_device(m);
+  shakti::set_field(m, field, src, is_device);
+  SHAKTI_CATCH
+}
+int shakti_get_field(shakti_model* m, int field, double* dst, int is_device) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(m, "null model");
+  use_device(m);
+  shakti::get_field(m, field, dst, is_device);
+  SHAKTI_CATCH
+}
+
+int shakti_set_flux(shakti_model* m, const double* q, int is_device) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(m && q, "null argument");
+  use_device(m);
+  const int64_t nv = m->hm.nv_g;
+  if (!m->stage2.p) m->stage2.alloc((size_t)3 * nv);
+  const double* src = q;
+  if (!is_device) {
+    SHAKTI_CUDA(cudaMemcpyAsync(m->stage2.p, q, sizeof(double) * 2 * nv, cudaMemcpyHostToDevice, m->stream));
+    src = m->stage2.p;
+  }
+  double* tmp = m->stage2.p + 2 * nv;
+  launch_deinterleave(nv, src, m->stage.p, tmp, m->stream);
+  scatter_in(m, m->stage.p, m->qx.p);
+  scatter_in(m, tmp, m->qy.p);
+  SHAKTI_CUDA(cudaStreamSynchronize(m->stream));
+  SHAKTI_CATCH
+}
+int shakti_get_flux(shakti_model* m, double* q, int is_device) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(m && q, "null argument");
+  use_device(m);
+  const int64_t nv = m->hm.nv_g;
+  if (!m->stage2.p) m->stage2.alloc((size_t)3 * nv);
+  double* tmp = m->stage2.p + 2 * nv;
+  gather_out(m, m->qx.p, m->stage.p);
+  gather_out(m, m->qy.p, tmp);
+  double* dst = is_device ? q : m->stage2.p;
+  launch_interleave(nv, m->stage.p, tmp, dst, m->stream);
+  if (!is_device) SHAKTI_CUDA(cudaMemcpyAsync(q, dst, sizeof(double) * 2 * nv, cudaMemcpyDeviceToHost, m->stream));
+  SHAKTI_CUDA(cudaStreamSynchronize(m->stream));
+  SHAKTI_CATCH
+}
+
+int shakti_set_dirichlet(shakti_model* m, const int32_t* dofs, int64_t n_dofs, double value) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(m && (dofs || n_dofs == 0) && n_dofs >= 0, "bad Dirichlet arguments");
+  use_device(m);
+  shakti::set_dirichlet(m, dofs, n_dofs, value);
+  SHAKTI_CATCH
+}
+
+int shakti_locate_dirichlet(shakti_model* m, const uint8_t* marker, int32_t* dofs, int64_t cap, int64_t* n_out) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(m && marker && n_out, "null argument");
+  std::vector<int32_t> d = locate_dirichlet_dofs(m->hm.nv_g, m->hm.ne_g, m->cells_g.data(), marker);
+  *n_out = (int64_t)d.size();
+  if (dofs) {
+    SHAKTI_REQUIRE(cap >= (int64_t)d.size(), "dof buffer too small");
+    std::copy(d.begin(), d.end(), dofs);
+  }
+  SHAKTI_CATCH
+}
+
+int shakti_set_quadrature(shakti_model* m, int32_t n_pts, const double* pts_xy, const double* wts) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(m && pts_xy && wts && n_pts > 0 && n_pts <= 64, "quadrature table must have 1..64 points");
+  use_device(m);
+  m->kq_pts.assign(pts_xy, pts_xy + 2 * n_pts);
+  m->kq_wts.assign(wts, wts + n_pts);
+  upload_k_rule(n_pts, pts_xy, wts, m->stream);
+  if (!m->dprm.n_is_3) upload_reaction_rule(n_pts, pts_xy, wts, m->stream);
+  SHAKTI_CATCH
+}
+
+int shakti_set_options(shakti_model* m, const shakti_options* opt) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(m && opt, "null argument");
+  use_device(m);
+  const bool amg_changed = opt->amg_max_levels != m->opt.amg_max_levels || opt->amg_coarse_size != m->opt.amg_coarse_size ||
+                           opt->amg_presmooth != m->opt.amg_presmooth || opt->amg_postsmooth != m->opt.amg_postsmooth ||
+                           opt->amg_smoother_omega != m->opt.amg_smoother_omega ||
+                           opt->amg_prolong_omega != m->opt.amg_prolong_omega;
+  SHAKTI_REQUIRE(opt->reorder == m->opt.reorder, "reorder can only be chosen at create time");
+  const int restart_old = m->opt.gmres_restart;
+  m->opt = *opt;
+  if (amg_changed) { m->amg.reset(); m->amg_setup_done = false; }
+  if (opt->gmres_restart != restart_old)
+    m->gmres.init(m->hm.n_owned, m->hm.n_local, std::max(2, opt->gmres_restart), m->sm_count, m->stream);
+  SHAKTI_CATCH
+}
+int shakti_get_options(shakti_model* m, shakti_options* opt) {
+  if (!m || !opt) return SHAKTI_ERR_INVALID;
+  *opt = m->opt;
+  return SHAKTI_OK;
+}
+int shakti_get_stats(shakti_model* m, shakti_stats* st) {
+  if (!m || !st) return SHAKTI_ERR_INVALID;
+  m->st.kernel_launches = g_kernel_launches - m->launches_at_create;
+  m->st.amg_levels = m->amg ? m->amg->levels() : 0;
+  m->st.amg_operator_complexity = m->amg ? m->amg->operator_complexity() : 0.0;
+  *st = m->st;
+  return SHAKTI_OK;
+}
+
+int shakti_get_csr(shakti_model* m, int32_t* rowptr, int32_t* col, int64_t* nnz) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(m && nnz, "null argument");
+  HostCsr& a = caller_pattern(m);
+  *nnz = a.nnz();
+  if (rowptr) std::copy(a.rowptr.begin(), a.rowptr.end(), rowptr);
+  if (col) std::copy(a.col.begin(), a.col.end(), col);
+  SHAKTI_CATCH
+}
+
+int shakti_kbar(shakti_model* m, double* out) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(m && out, "null argument");
+  use_device(m);
+  compute_kbar(m);
+  std::vector<double> k = m->kbar.download(m->stream);
+  for (int64_t e = 0; e < m->hm.ne_g; ++e) out[e] = 0.0;
+  for (int32_t e = 0; e < m->hm.ne; ++e) out[m->hm.cell_l2g[e]] = k[e];
+  SHAKTI_CATCH
+}
+
+int shakti_assemble(shakti_model* m, double dt, double* F_out, double* Jvals_out) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(m && dt > 0, "bad arguments");
+  use_device(m);
+  compute_kbar(m);
+  assemble(m, dt, 1);
+  if (F_out) shakti::get_field(m, SHAKTI_F_RESIDUAL, F_out, 0);
+  if (Jvals_out) {
+    HostCsr& a = caller_pattern(m);
+    std::vector<double> v = m->J.val.download(m->stream);
+    std::fill(Jvals_out, Jvals_out + a.nnz(), 0.0);
+    const HostMesh& hm = m->hm;
+    for (int32_t r = 0; r < hm.n_owned; ++r) {
+      const int32_t gr = hm.l2g[r];
+      const int32_t* b = a.col.data() + a.rowptr[gr];
+      const int32_t* e = a.col.data() + a.rowptr[gr + 1];
+      for (int32_t k = hm.A.rowptr[r]; k < hm.A.rowptr[r + 1]; ++k) {
+        const int32_t gc = hm.l2g[hm.A.col[k]];
+        const int32_t* p = std::lower_bound(b, e, gc);
+        Jvals_out[p - a.col.data()] = v[hm.S.pos(r, k - hm.A.rowptr[r])];
+      }
+    }
+  }
+  SHAKTI_CATCH
+}
+
+int shakti_spmv(shakti_model* m, const double* x, double* y) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(m && x && y, "null argument");
+  use_device(m);
+  SHAKTI_REQUIRE(m->J_valid, "no assembled Jacobian");
+  SHAKTI_CUDA(cudaMemcpyAsync(m->stage.p, x, sizeof(double) * m->hm.nv_g, cudaMemcpyHostToDevice, m->stream));
+  scatter_in(m, m->stage.p, m->b2.p);   // b2 is scratch outside update_b
+  launch_spmv(view(m->J), m->b2.p, m->rhs.p, m->stream);
+  gather_out(m, m->rhs.p, m->stage.p);
+  SHAKTI_CUDA(cudaMemcpyAsync(y, m->stage.p, sizeof(double) * m->hm.nv_g, cudaMemcpyDeviceToHost, m->stream));
+  SHAKTI_CUDA(cudaStreamSynchronize(m->stream));
+  SHAKTI_CATCH
+}
+
+int shakti_linear_solve(shakti_model* m, const double* rhs, double* dx, int32_t* iters, double* relres) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(m && rhs && dx, "null argument");
+  use_device(m);
+  SHAKTI_CUDA(cudaMemcpyAsync(m->stage.p, rhs, sizeof(double) * m->hm.nv_g, cudaMemcpyHostToDevice, m->stream));
+  scatter_in(m, m->stage.p, m->b2.p);
+  // interior system: Dirichlet rows are identity
+  launch_xmy_masked(m->hm.n_owned, m->b2.p, m->isbc.p, m->rhs.p, m->stream);
+  KrylovResult r = linear_solve(m, m->rhs.p, m->dx.p);
+  if (m->n_bc)
+    SHAKTI_LAUNCH(fix_bc_dx_kernel, div_up(m->hm.n_owned, 256), 256, 0, m->stream, m->hm.n_owned, m->isbc.p, m->b2.p, m->dx.p);
+  gather_out(m, m->dx.p, m->stage.p);
+  SHAKTI_CUDA(cudaMemcpyAsync(dx, m->stage.p, sizeof(double) * m->hm.nv_g, cudaMemcpyDeviceToHost, m->stream));
+  SHAKTI_CUDA(cudaStreamSynchronize(m->stream));
+  if (iters) *iters = r.iterations;
+  if (relres) *relres = r.relres;
+  if (!r.converged) throw Error(SHAKTI_ERR_LINEAR, "Krylov solve did not reach its tolerance");
+  SHAKTI_CATCH
+}
+
+int shakti_get_winning_cells(shakti_model* m, int32_t* win_cell) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(m && win_cell, "null argument");
+  for (int64_t i = 0; i < m->hm.nv_g; ++i) win_cell[i] = -1;
+  for (int32_t r = 0; r < m->hm.n_owned; ++r) win_cell[m->hm.l2g[r]] = m->hm.win_cell[r];
+  SHAKTI_CATCH
+}
+
+int shakti_start(shakti_model* m) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(m, "null model");
+  use_device(m);
+  SHAKTI_CUDA(cudaMemcpyAsync(m->N.p, m->N_n.p, sizeof(double) * m->hm.n_local, cudaMemcpyDeviceToDevice, m->stream));
+  SHAKTI_CATCH
+}
+
+int shakti_newton_solve(shakti_model* m, double dt, int32_t* niter, int32_t* converged) {
+  int32_t it = 0, cv = 0;
+  if (niter) *niter = 0;
+  if (converged) *converged = 0;
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(m && dt > 0, "bad arguments");
+  use_device(m);
+  try {
+    newton_solve(m, dt, &it, &cv);
+  } catch (...) {
+    if (niter) *niter = it;
+    throw;
+  }
+  if (niter) *niter = it;
+  if (converged) *converged = cv;
+  SHAKTI_CATCH
+}
+int shakti_update_q(shakti_model* m) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(m, "null model");
+  use_device(m);
+  update_q(m);
+  SHAKTI_CATCH
+}
+int shakti_update_melt(shakti_model* m) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(m, "null model");
+  use_device(m);
+  update_melt(m);
+  SHAKTI_CATCH
+}
+int shakti_update_b(shakti_model* m, double dt) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(m && dt > 0, "bad arguments");
+  use_device(m);
+  update_b(m, dt);
+  SHAKTI_CATCH
+}
+int shakti_copy_N_to_N_n(shakti_model* m) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(m, "null model");
+  use_device(m);
+  copy_N(m);
+  SHAKTI_CATCH
+}
+int shakti_step(shakti_model* m, double dt, int32_t* niter, int32_t* converged) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(m, "null model");
+  use_device(m);
+  shakti::step(m, dt, niter, converged);
+  SHAKTI_CATCH
+}
+int shakti_run(shakti_model* m, const double* dts, int64_t nsteps, int32_t* niter_out) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(m && dts && nsteps >= 0, "bad arguments");
+  use_device(m);
+  for (int64_t i = 0; i < nsteps; ++i) {
+    int32_t it = 0, cv = 0;
+    shakti::step(m, dts[i], &it, &cv);
+    if (niter_out) niter_out[i] = it;
+  }
+  SHAKTI_CUDA(cudaStreamSynchronize(m->stream));
+  SHAKTI_CATCH
+}
+
+int shakti_step_host(shakti_model* m, double dt, const double* inputs_host, double* b_out, double* N_out,
+                     double* qx_out, double* qy_out, int32_t* niter, int32_t* converged) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(m, "null model");
+  use_device(m);
+  if (inputs_host) shakti::set_field(m, SHAKTI_F_INPUTS, inputs_host, 0);
+  shakti::step(m, dt, niter, converged);
+  if (b_out) shakti::get_field(m, SHAKTI_F_B, b_out, 0);
+  if (N_out) shakti::get_field(m, SHAKTI_F_N, N_out, 0);
+  if (qx_out) shakti::get_field(m, SHAKTI_F_QX, qx_out, 0);
+  if (qy_out) shakti::get_field(m, SHAKTI_F_QY, qy_out, 0);
+  SHAKTI_CATCH
+}
+
+int shakti_kernel_bytes(shakti_model* m, int which, double* bytes) {
+  if (!m || !bytes) return SHAKTI_ERR_INVALID;
+  const double nv = (double)m->hm.n_local, no = (double)m->hm.n_owned, ne = (double)m->hm.ne, nnz = (double)m->hm.A.nnz();
+  switch (which) {
+    case 0: *bytes = 12.0 * nnz + 20.0 * no; break;                                    // SpMV
+    case 1: *bytes = 12.0 * ne + 8.0 * 12.0 * nv + 8.0 * ne + 8.0 * nnz + 8.0 * no; break;  // F+J assembly
+    case 2: *bytes = 12.0 * ne + 8.0 * 5.0 * nv + 8.0 * ne; break;                      // Kbar
+    case 3: *bytes = 12.0 * ne + 8.0 * 13.0 * nv; break;                                // nodal updates
+    case 4: *bytes = 16.0 * no; break;                                                  // dot
+    case 5: *bytes = 24.0 * no; break;                                                  // axpy
+    default: return SHAKTI_ERR_INVALID;
+  }
+  return SHAKTI_OK;
+}
+
+int shakti_time_kernel(shakti_model* m, int which, int reps, double dt, double* ms_per_launch) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(m && ms_per_launch && reps > 0, "bad arguments");
+  use_device(m);
+  refresh_h0(m);
+  cudaEvent_t e0, e1;
+  SHAKTI_CUDA(cudaEventCreate(&e0));
+  SHAKTI_CUDA(cudaEventCreate(&e1));
+  auto once = [&]() {
+    switch (which) {
+      case 0: launch_spmv(view(m->J), m->dx.p, m->rhs.p, m->stream); break;
+      case 1: assemble(m, dt, 1); break;
+      case 2: compute_kbar(m); break;
+      case 3:
+        // same kernels as a step, on scratch outputs so the state is untouched
+        launch_update_melt(m->hm.n_owned, m->win.p, m->x.p, m->y.p, m->h0.p, m->N.p, m->b.p, m->qx.p, m->qy.p, m->G.p, m->melt.p, m->melt2.p, m->dprm, m->stream);
+        launch_update_b(m->hm.n_owned, m->win.p, m->x.p, m->y.p, m->h0.p, m->N.p, m->b.p, m->qx.p, m->qy.p, m->G.p, m->melt.p, m->b2.p, dt, m->opt.b_min, m->dprm, m->stream);
+        break;
+      case 4: launch_multi_dot(m->red, m->hm.n_owned, 1, m->dx.p, m->hm.n_owned, m->rhs.p, m->scal.p, m->stream); break;
+      case 5: launch_axpy(m->hm.n_owned, 0.0, m->dx.p, m->rhs.p, m->stream); break;
+      default: throw Error(SHAKTI_ERR_INVALID, "unknown kernel id");
+    }
+  };
+  if (which == 0) SHAKTI_REQUIRE(m->J_valid, "no assembled Jacobian");
+  if (which == 1) compute_kbar(m);
+  once();
+  SHAKTI_CUDA(cudaEventRecord(e0, m->stream));
+  for (int i = 0; i < reps; ++i) once();
+  SHAKTI_CUDA(cudaEventRecord(e1, m->stream));
+  SHAKTI_CUDA(cudaEventSynchronize(e1));
+  float ms = 0;
+  SHAKTI_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_per_launch = (double)ms / reps;
+  SHAKTI_CATCH
+}
+
+int shakti_comm_unique_id(uint8_t id[128]) {
+  SHAKTI_TRY
+  comm_unique_id(id);
+  SHAKTI_CATCH
+}
+int shakti_comm_init(const uint8_t id[128], int rank, int nranks, int device) {
+  SHAKTI_TRY
+  comm_init(id, rank, nranks, device);
+  SHAKTI_CATCH
+}
+int shakti_comm_finalize(void) {
+  SHAKTI_TRY
+  comm_finalize();
+  SHAKTI_CATCH
+}
+int shakti_get_owned(shakti_model* m, int32_t* ids, int64_t* n_owned) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(m && n_owned, "null argument");
+  *n_owned = m->hm.n_owned;
+  if (ids) std::copy(m->hm.l2g.begin(), m->hm.l2g.begin() + m->hm.n_owned, ids);
+  SHAKTI_CATCH
+}
+
+// ---------------------------------------------------------------- host-side helpers
+struct shakti_host_mesh { shakti::HostMesh hm; };
+
+int shakti_host_csr_pattern(int64_t n_vert, int64_t n_cell, const int32_t* cells, int32_t* rowptr, int32_t* col,
+                            int64_t* nnz) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(cells && nnz && n_vert > 0 && n_cell > 0, "bad arguments");
+  HostCsr a = caller_csr(n_vert, n_cell, cells);
+  *nnz = a.nnz();
+  if (rowptr) std::copy(a.rowptr.begin(), a.rowptr.end(), rowptr);
+  if (col) std::copy(a.col.begin(), a.col.end(), col);
+  SHAKTI_CATCH
+}
+int shakti_host_locate_dirichlet(int64_t n_vert, int64_t n_cell, const int32_t* cells, const uint8_t* marker,
+                                 int32_t* dofs, int64_t cap, int64_t* n_out) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(cells && marker && n_out, "null argument");
+  std::vector<int32_t> d = locate_dirichlet_dofs(n_vert, n_cell, cells, marker);
+  *n_out = (int64_t)d.size();
+  if (dofs) {
+    SHAKTI_REQUIRE(cap >= (int64_t)d.size(), "dof buffer too small");
+    std::copy(d.begin(), d.end(), dofs);
+  }
+  SHAKTI_CATCH
+}
+int shakti_host_mesh_create(int64_t n_vert, int64_t n_cell, const double* xy, const int32_t* cells, int rank,
+                            int nranks, int reorder, shakti_host_mesh** out) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(xy && cells && out && nranks >= 1 && rank >= 0 && rank < nranks, "bad arguments");
+  std::unique_ptr<shakti_host_mesh> h(new shakti_host_mesh());
+  build_host_mesh(n_vert, n_cell, xy, cells, rank, nranks, reorder, h->hm);
+  *out = h.release();
+  SHAKTI_CATCH
+}
+int shakti_host_mesh_destroy(shakti_host_mesh* hm) {
+  delete hm;
+  return SHAKTI_OK;
+}
+int shakti_host_mesh_info(shakti_host_mesh* h, int64_t info[6]) {
+  if (!h || !info) return SHAKTI_ERR_INVALID;
+  info[0] = h->hm.n_owned; info[1] = h->hm.n_local; info[2] = h->hm.ne; info[3] = h->hm.A.nnz();
+  info[4] = h->hm.S.padded(); info[5] = (int64_t)h->hm.nbrs.size();
+  return SHAKTI_OK;
+}
+int shakti_host_mesh_array(shakti_host_mesh* h, int which, int32_t* out, int64_t* n) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(h && n, "null argument");
+  const HostMesh& m = h->hm;
+  std::vector<int32_t> tmp;
+  const std::vector<int32_t>* v = nullptr;
+  switch (which) {
+    case SHAKTI_HM_L2G: v = &m.l2g; break;
+    case SHAKTI_HM_CELLS: v = &m.cells; break;
+    case SHAKTI_HM_CELL_L2G: v = &m.cell_l2g; break;
+    case SHAKTI_HM_ROWPTR: v = &m.A.rowptr; break;
+    case SHAKTI_HM_COL: v = &m.A.col; break;
+    case SHAKTI_HM_SLICE_PTR: v = &m.S.slice_ptr; break;
+    case SHAKTI_HM_SELL_COL: v = &m.S.col; break;
+    case SHAKTI_HM_SLOT: v = &m.slot; break;
+    case SHAKTI_HM_DIAG_POS: v = &m.diag_pos; break;
+    case SHAKTI_HM_WIN: v = &m.win; break;
+    case SHAKTI_HM_WIN_CELL: v = &m.win_cell; break;
+    case SHAKTI_HM_NBR_RANK:
+      for (const auto& nb : m.nbrs) tmp.push_back(nb.rank);
+      v = &tmp; break;
+    case SHAKTI_HM_NBR_SEND_PTR:
+      tmp.push_back(0);
+      for (const auto& nb : m.nbrs) tmp.push_back(tmp.back() + (int32_t)nb.send_local.size());
+      v = &tmp; break;
+    case SHAKTI_HM_NBR_SEND_IDX:
+      for (const auto& nb : m.nbrs) tmp.insert(tmp.end(), nb.send_local.begin(), nb.send_local.end());
+      v = &tmp; break;
+    case SHAKTI_HM_NBR_RECV:
+      for (const auto& nb : m.nbrs) { tmp.push_back(nb.recv_begin); tmp.push_back(nb.recv_count); }
+      v = &tmp; break;
+    default: throw Error(SHAKTI_ERR_INVALID, "unknown host array id");
+  }
+  if (out) {
+    SHAKTI_REQUIRE(*n >= (int64_t)v->size(), "array buffer too small");
+    std::copy(v->begin(), v->end(), out);
+  }
+  *n = (int64_t)v->size();
+  SHAKTI_CATCH
+}
+
+}  // extern "C"

@@ -1,0 +1,106 @@
+// Device-side data structures and kernel launch wrappers.
+#pragma once
+#include "common.h"
+#include "prep.h"
+
+namespace shakti {
+
+// constants of source/params.py:4-11 plus derived values, passed to kernels by value
+struct DevParams {
+  double g, rho_i, rho_w, nu, Lh, omega, n, A;
+  double cm;    // 1/rho_i - 1/rho_w
+  double rwg;   // rho_w * g
+  int n_is_3;   // Glen exponent is exactly 3 => closure terms are polynomials
+};
+
+DevParams make_dev_params(const shakti_params& p);
+
+// SELL-32 sparse matrix on the device (layout: prep.h HostSell)
+struct DevSell {
+  int32_t n_rows = 0, n_cols = 0, n_slices = 0;
+  int64_t padded = 0, nnz = 0;
+  DevBuf<int32_t> slice_ptr, col, rowlen;
+  DevBuf<double> val;
+  void upload_pattern(const HostSell& h, int64_t nnz_);
+};
+
+struct SellView {
+  int32_t n_rows, n_slices;
+  const int32_t* slice_ptr;
+  const int32_t* col;
+  const double* val;
+};
+inline SellView view(const DevSell& a) { return {a.n_rows, a.n_slices, a.slice_ptr.p, a.col.p, a.val.p}; }
+
+// Pointers of the vertex fields the element kernels read (all n_local long)
+struct FieldPtrs {
+  const double *x, *y, *h0, *N, *N_n, *b, *qx, *qy, *G, *melt, *storage, *inputs;
+  const uint8_t* isbc;
+};
+
+// ---- quadrature tables in __constant__ memory
+void upload_k_rule(int n, const double* pts_xy, const double* wts, cudaStream_t s);       // for Kbar
+void upload_reaction_rule(int n, const double* pts_xy, const double* wts, cudaStream_t s); // closure/storage
+
+// ---- element kernels
+void launch_kbar(int32_t ne, const int32_t* c0, const int32_t* c1, const int32_t* c2,
+                 const double* x, const double* y, const double* b, const double* qx,
+                 const double* qy, double* kbar, DevParams p, cudaStream_t s);
+void launch_assemble_atomic(int32_t ne, int32_t n_owned, const int32_t* c0, const int32_t* c1,
+                            const int32_t* c2, const int32_t* slot, FieldPtrs f, const double* kbar,
+                            double dt, double N_bdry, double* F, double* Jval, int want_J,
+                            DevParams p, cudaStream_t s);
+void launch_apply_bc(int32_t n_owned, const uint8_t* isbc, const double* N, double N_bdry,
+                     const int32_t* diag_pos, double* F, double* Jval, int want_J, cudaStream_t s);
+
+// ---- nodal updates (solvers.py:186-197)
+void launch_update_q(int32_t n_owned, const int32_t* win, const double* x, const double* y,
+                     const double* h0, const double* N, const double* b, double* qx, double* qy,
+                     DevParams p, cudaStream_t s);
+void launch_update_melt(int32_t n_owned, const int32_t* win, const double* x, const double* y,
+                        const double* h0, const double* N, const double* b, const double* qx,
+                        const double* qy, const double* G, const double* melt_old, double* melt_new,
+                        DevParams p, cudaStream_t s);
+void launch_update_b(int32_t n_owned, const int32_t* win, const double* x, const double* y,
+                     const double* h0, const double* N, const double* b_old, const double* qx,
+                     const double* qy, const double* G, const double* melt, double* b_new, double dt,
+                     double b_min, DevParams p, cudaStream_t s);
+
+// ---- sparse / vector kernels
+void launch_spmv(SellView A, const double* x, double* y, cudaStream_t s);                      // y = A x
+void launch_residual(SellView A, const double* x, const double* b, double* r, cudaStream_t s); // r = b - A x
+// x_out = x + omega * dinv .* (b - A x)
+void launch_jacobi(SellView A, const double* dinv, const double* b, const double* x, double* x_out,
+                   double omega, cudaStream_t s);
+void launch_spmv_add(SellView A, const double* x, double* y, cudaStream_t s);                  // y += A x
+void launch_extract_dinv(int32_t n, const int32_t* diag_pos, const double* val, double* dinv, cudaStream_t s);
+
+// reductions: out[k] = <V_k, w>, V_k = V + k*ld, k < nvec; result in device memory `out`
+struct Reducer {
+  DevBuf<double> partial;
+  DevBuf<unsigned int> counter;
+  int max_blocks = 0;
+  void init(int sm_count);
+};
+void launch_multi_dot(Reducer& red, int64_t n, int nvec, const double* V, int64_t ld, const double* w,
+                      double* out, cudaStream_t s);
+// w -= sum_k h[k] V_k   (h on device)
+void launch_multi_axpy_neg(int64_t n, int nvec, const double* V, int64_t ld, const double* h, double* w,
+                           cudaStream_t s);
+// y = sum_k h[k] V_k
+void launch_combine(int64_t n, int nvec, const double* V, int64_t ld, const double* h, double* y,
+                    cudaStream_t s);
+// y = alpha_dev[0] * x (alpha read from device), optional reciprocal
+void launch_scale_dev(int64_t n, const double* x, const double* alpha_dev, int reciprocal, double* y,
+                      cudaStream_t s);
+void launch_axpy(int64_t n, double alpha, const double* x, double* y, cudaStream_t s);  // y += alpha x
+void launch_xmy_masked(int64_t n, const double* a, const uint8_t* mask, double* out, cudaStream_t s);
+void launch_pointwise_mul(int64_t n, const double* a, const double* b, double scale, double* out, cudaStream_t s);
+void launch_fill(int64_t n, double v, double* x, cudaStream_t s);
+void launch_gather(int64_t n, const int32_t* idx, const double* src, double* dst, cudaStream_t s);   // dst[i] = src[idx[i]]
+void launch_scatter(int64_t n, const int32_t* idx, const double* src, double* dst, cudaStream_t s);  // dst[idx[i]] = src[i]
+void launch_head0(int64_t n, const double* z_b, const double* z_s, double ratio, double* h0, cudaStream_t s);
+void launch_interleave(int64_t n, const double* a, const double* b, double* ab, cudaStream_t s);
+void launch_deinterleave(int64_t n, const double* ab, double* a, double* b, cudaStream_t s);
+
+}  // namespace shakti

@@ -1,0 +1,690 @@
+// Hand-written sm_100a kernels of the SHAKTI hot path: transmissivity integral, residual +
+// Jacobian assembly, nodal updates, SELL SpMV family and the vector kernels of the Krylov
+// solvers.  All fp64 / int32, HBM-bandwidth bound by design (no tensor cores: nothing here is
+// a dense contraction).  Reference formulas: source/constitutive.py:6-31, source/solvers.py:35-45.
+#include "device.h"
+
+namespace shakti {
+
+int64_t g_kernel_launches = 0;
+
+DevParams make_dev_params(const shakti_params& p) {
+  DevParams d;
+  d.g = p.g; d.rho_i = p.rho_i; d.rho_w = p.rho_w; d.nu = p.nu; d.Lh = p.Lh;
+  d.omega = p.omega; d.n = p.n; d.A = p.A;
+  d.cm = 1.0 / p.rho_i - 1.0 / p.rho_w;
+  d.rwg = p.rho_w * p.g;
+  d.n_is_3 = (p.n == 3.0);
+  return d;
+}
+
+void DevSell::upload_pattern(const HostSell& h, int64_t nnz_) {
+  n_rows = (int32_t)h.n_rows; n_cols = (int32_t)h.n_cols; n_slices = (int32_t)h.n_slices;
+  padded = h.padded(); nnz = nnz_;
+  slice_ptr.upload(h.slice_ptr);
+  col.upload(h.col);
+  rowlen.upload(h.rowlen);
+  val.alloc_zero(padded);
+}
+
+// ------------------------------------------------------------------ quadrature tables
+constexpr int kMaxQ = 64;
+__constant__ double c_kq[4 * kMaxQ];   // l0,l1,l2,w per point: rule for the K integral
+__constant__ int c_nkq;
+__constant__ double c_rq[4 * kMaxQ];   // rule for the closure/storage (reaction) integrals
+__constant__ int c_nrq;
+
+static void pack_rule(int n, const double* pts, const double* wts, double* out) {
+  for (int k = 0; k < n; ++k) {
+    out[4 * k + 0] = 1.0 - pts[2 * k] - pts[2 * k + 1];
+    out[4 * k + 1] = pts[2 * k];
+    out[4 * k + 2] = pts[2 * k + 1];
+    out[4 * k + 3] = wts[k];
+  }
+}
+void upload_k_rule(int n, const double* pts, const double* wts, cudaStream_t s) {
+  SHAKTI_REQUIRE(n > 0 && n <= kMaxQ, "quadrature table must have 1..64 points");
+  double h[4 * kMaxQ];
+  pack_rule(n, pts, wts, h);
+  SHAKTI_CUDA(cudaStreamSynchronize(s));
+  SHAKTI_CUDA(cudaMemcpyToSymbol(c_kq, h, sizeof(double) * 4 * n));
+  SHAKTI_CUDA(cudaMemcpyToSymbol(c_nkq, &n, sizeof(int)));
+}
+void upload_reaction_rule(int n, const double* pts, const double* wts, cudaStream_t s) {
+  SHAKTI_REQUIRE(n > 0 && n <= kMaxQ, "quadrature table must have 1..64 points");
+  double h[4 * kMaxQ];
+  pack_rule(n, pts, wts, h);
+  SHAKTI_CUDA(cudaStreamSynchronize(s));
+  SHAKTI_CUDA(cudaMemcpyToSymbol(c_rq, h, sizeof(double) * 4 * n));
+  SHAKTI_CUDA(cudaMemcpyToSymbol(c_nrq, &n, sizeof(int)));
+}
+
+// ------------------------------------------------------------------ element geometry
+struct Geo {
+  double gx[3], gy[3];  // grad phi_a
+  double detabs;        // |det J| = 2 |T|
+};
+
+__device__ __forceinline__ Geo geometry(double x0, double y0, double x1, double y1, double x2, double y2) {
+  Geo g;
+  const double d1x = x1 - x0, d1y = y1 - y0, d2x = x2 - x0, d2y = y2 - y0;
+  const double det = d1x * d2y - d2x * d1y;
+  const double inv = 1.0 / det;
+  g.gx[1] = d2y * inv;  g.gy[1] = -d2x * inv;
+  g.gx[2] = -d1y * inv; g.gy[2] = d1x * inv;
+  g.gx[0] = -g.gx[1] - g.gx[2];
+  g.gy[0] = -g.gy[1] - g.gy[2];
+  g.detabs = fabs(det);
+  return g;
+}
+
+__device__ __forceinline__ double powabs(double a, double e, int e_is_2) {
+  // |a|^e ; the n == 3 fast path keeps closure terms polynomial (abs(N)**(n-1), constitutive.py:31)
+  return e_is_2 ? a * a : pow(fabs(a), e);
+}
+
+// ------------------------------------------------------------------ Kbar
+// Kbar_T = |detJ| sum_k w_k K(b(xi_k), |q(xi_k)|),  K = |b|^3 g / (12 nu (1 + omega Re)),
+// Re = sqrt(q.q)/nu   (constitutive.py:11-20).  One thread per cell; compute heavy
+// (nq x (sqrt + div)) but executed once per time step because b, q are lagged (solvers.py:37-45).
+__global__ void __launch_bounds__(256)
+kbar_kernel(int32_t ne, const int32_t* __restrict__ c0, const int32_t* __restrict__ c1,
+            const int32_t* __restrict__ c2, const double* __restrict__ x, const double* __restrict__ y,
+            const double* __restrict__ b, const double* __restrict__ qx, const double* __restrict__ qy,
+            double* __restrict__ kbar, DevParams p) {
+  const int32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  const int32_t v0 = c0[e], v1 = c1[e], v2 = c2[e];
+  const double x0 = x[v0], y0 = y[v0], x1 = x[v1], y1 = y[v1], x2 = x[v2], y2 = y[v2];
+  const double detabs = fabs((x1 - x0) * (y2 - y0) - (x2 - x0) * (y1 - y0));
+  const double b0 = b[v0], b1 = b[v1], b2 = b[v2];
+  const double qx0 = qx[v0], qx1 = qx[v1], qx2 = qx[v2];
+  const double qy0 = qy[v0], qy1 = qy[v1], qy2 = qy[v2];
+  const double cK = p.g / (12.0 * p.nu);
+  const double cRe = p.omega / p.nu;
+  double acc = 0.0;
+  const int nq = c_nkq;
+  for (int k = 0; k < nq; ++k) {
+    const double l0 = c_kq[4 * k], l1 = c_kq[4 * k + 1], l2 = c_kq[4 * k + 2], w = c_kq[4 * k + 3];
+    const double bq = fabs(l0 * b0 + l1 * b1 + l2 * b2);
+    const double u = l0 * qx0 + l1 * qx1 + l2 * qx2;
+    const double v = l0 * qy0 + l1 * qy1 + l2 * qy2;
+    const double qn = sqrt(u * u + v * v);
+    acc += w * (bq * bq * bq) * cK / (1.0 + cRe * qn);
+  }
+  kbar[e] = acc * detabs;
+}
+
+void launch_kbar(int32_t ne, const int32_t* c0, const int32_t* c1, const int32_t* c2, const double* x,
+                 const double* y, const double* b, const double* qx, const double* qy, double* kbar,
+                 DevParams p, cudaStream_t s) {
+  if (ne == 0) return;
+  SHAKTI_LAUNCH(kbar_kernel, div_up(ne, 256), 256, 0, s, ne, c0, c1, c2, x, y, b, qx, qy, kbar, p);
+}
+
+// ------------------------------------------------------------------ element residual + Jacobian
+// F_a  = Kbar (grad h . grad phi_a) + int [c_m Melt - Closure - storage/(rho_w g dt)(N-N_n) - inputs] phi_a
+// J_ab = -Kbar/(rho_w g) grad phi_a.grad phi_b
+//        + int [ c_m (q.grad phi_b)/Lh - (dClosure/dN + storage/(rho_w g dt)) phi_b ] phi_a
+// (solvers.py:35-45,51).  grad h, grad b, grad melt are cell constants, so the Melt and inputs
+// parts are P1 functions integrated in closed form (int phi_a phi_b = |detJ|/24 (1+delta_ab));
+// closure (degree 5 for n = 3) and storage use the reaction rule in __constant__ memory.
+struct ElemOut {
+  double F[3];
+  double J[3][3];
+};
+
+__device__ __forceinline__ void element_FJ(const int32_t v[3], const FieldPtrs& f, double kb, double dt,
+                                           const DevParams& p, ElemOut& o, double Nv[3]) {
+  const Geo g = geometry(f.x[v[0]], f.y[v[0]], f.x[v[1]], f.y[v[1]], f.x[v[2]], f.y[v[2]]);
+  double h[3], bb[3], mm[3], qxv[3], qyv[3], Nn[3], st[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    Nv[i] = f.N[v[i]];
+    h[i] = f.h0[v[i]] - Nv[i] / p.rwg;
+    bb[i] = f.b[v[i]];
+    mm[i] = f.melt[v[i]];
+    qxv[i] = f.qx[v[i]];
+    qyv[i] = f.qy[v[i]];
+    Nn[i] = f.N_n[v[i]];
+    st[i] = f.storage[v[i]];
+  }
+  double ghx = 0, ghy = 0, gbx = 0, gby = 0, gmx = 0, gmy = 0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    ghx += h[i] * g.gx[i];  ghy += h[i] * g.gy[i];
+    gbx += bb[i] * g.gx[i]; gby += bb[i] * g.gy[i];
+    gmx += mm[i] * g.gx[i]; gmy += mm[i] * g.gy[i];
+  }
+  const double gb2 = gbx * gbx + gby * gby;
+  const double gmgb = gmx * gbx + gmy * gby;
+  const double inv1 = 1.0 / (1.0 + gb2);
+  // nodal values of the P1 part of the reaction integrand
+  double rl[3], rsum = 0, qxs = 0, qys = 0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double m0 = (f.G[v[i]] - p.rwg * (qxv[i] * ghx + qyv[i] * ghy)) / p.Lh;   // constitutive.py:25
+    const double md = (gb2 * mm[i] + bb[i] * gmgb) * inv1;                           // constitutive.py:26
+    rl[i] = p.cm * (m0 + md) - f.inputs[v[i]];
+    rsum += rl[i];
+    qxs += qxv[i];
+    qys += qyv[i];
+  }
+  const double m24 = g.detabs * (1.0 / 24.0);
+  const double kJ = -kb / p.rwg;
+  const double cadv = p.cm / p.Lh * m24;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    o.F[a] = kb * (ghx * g.gx[a] + ghy * g.gy[a]) + m24 * (rsum + rl[a]);
+    const double qax = cadv * (qxs + qxv[a]), qay = cadv * (qys + qyv[a]);
+#pragma unroll
+    for (int b = 0; b < 3; ++b)
+      o.J[a][b] = kJ * (g.gx[a] * g.gx[b] + g.gy[a] * g.gy[b]) + qax * g.gx[b] + qay * g.gy[b];
+  }
+  // closure + storage by quadrature
+  const double cs = 1.0 / (p.rwg * dt);
+  const double e1 = p.n - 1.0, e2 = p.n - 2.0;
+  double f0 = 0, f1 = 0, f2 = 0, m00 = 0, m01 = 0, m02 = 0, m11 = 0, m12 = 0, m22 = 0;
+  const int nq = c_nrq;
+  for (int k = 0; k < nq; ++k) {
+    const double l0 = c_rq[4 * k], l1 = c_rq[4 * k + 1], l2 = c_rq[4 * k + 2];
+    const double w = c_rq[4 * k + 3] * g.detabs;
+    const double bq = l0 * bb[0] + l1 * bb[1] + l2 * bb[2];
+    const double Nq = l0 * Nv[0] + l1 * Nv[1] + l2 * Nv[2];
+    const double dq = Nq - (l0 * Nn[0] + l1 * Nn[1] + l2 * Nn[2]);
+    const double sq = (l0 * st[0] + l1 * st[1] + l2 * st[2]) * cs;
+    double clos, dclos;
+    if (p.n_is_3) {
+      const double N2 = Nq * Nq;                  // abs(N)**2
+      clos = p.A * bq * Nq * N2;
+      dclos = p.A * bq * (N2 + Nq * 2.0 * fabs(Nq) * (Nq > 0 ? 1.0 : (Nq < 0 ? -1.0 : 0.0)));
+    } else {
+      const double sgn = Nq > 0 ? 1.0 : (Nq < 0 ? -1.0 : 0.0);
+      const double p1 = pow(fabs(Nq), e1);
+      clos = p.A * bq * Nq * p1;
+      dclos = p.A * bq * (p1 + Nq * e1 * pow(fabs(Nq), e2) * sgn);
+    }
+    const double r = w * (clos + sq * dq);
+    const double d = w * (dclos + sq);
+    f0 += r * l0; f1 += r * l1; f2 += r * l2;
+    const double d0 = d * l0, d1 = d * l1;
+    m00 += d0 * l0; m01 += d0 * l1; m02 += d0 * l2;
+    m11 += d1 * l1; m12 += d1 * l2; m22 += d * l2 * l2;
+  }
+  o.F[0] -= f0; o.F[1] -= f1; o.F[2] -= f2;
+  o.J[0][0] -= m00; o.J[0][1] -= m01; o.J[0][2] -= m02;
+  o.J[1][0] -= m01; o.J[1][1] -= m11; o.J[1][2] -= m12;
+  o.J[2][0] -= m02; o.J[2][1] -= m12; o.J[2][2] -= m22;
+}
+
+// Dirichlet lifting (scale -1: F += J_full (g - x) on bc columns) applied in place.
+__device__ __forceinline__ void apply_lifting(ElemOut& o, const double Nv[3], const bool bc[3], double N_bdry) {
+#pragma unroll
+  for (int b = 0; b < 3; ++b)
+    if (bc[b]) {
+      const double gx = N_bdry - Nv[b];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) o.F[a] += o.J[a][b] * gx;
+    }
+}
+
+// Variant 1: one thread per cell, scatter with fp64 atomics into the SELL value array through
+// the precomputed (cell, a, b) -> position table.  F and Jval must be zeroed beforehand.
+__global__ void __launch_bounds__(128)
+assemble_atomic_kernel(int32_t ne, int32_t n_owned, const int32_t* __restrict__ c0,
+                       const int32_t* __restrict__ c1, const int32_t* __restrict__ c2,
+                       const int32_t* __restrict__ slot, FieldPtrs f, const double* __restrict__ kbar,
+                       double dt, double N_bdry, double* __restrict__ F, double* __restrict__ Jval,
+                       int want_J, DevParams p) {
+  const int32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  const int32_t v[3] = {c0[e], c1[e], c2[e]};
+  ElemOut o;
+  double Nv[3];
+  element_FJ(v, f, kbar[e], dt, p, o, Nv);
+  const bool bc[3] = {f.isbc[v[0]] != 0, f.isbc[v[1]] != 0, f.isbc[v[2]] != 0};
+  apply_lifting(o, Nv, bc, N_bdry);
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    if (v[a] >= n_owned || bc[a]) continue;   // owner computes; bc rows are set by apply_bc
+    atomicAdd(&F[v[a]], o.F[a]);
+    if (want_J) {
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+        if (!bc[b]) atomicAdd(&Jval[slot[(size_t)(3 * a + b) * ne + e]], o.J[a][b]);
+    }
+  }
+}
+
+void launch_assemble_atomic(int32_t ne, int32_t n_owned, const int32_t* c0, const int32_t* c1,
+                            const int32_t* c2, const int32_t* slot, FieldPtrs f, const double* kbar,
+                            double dt, double N_bdry, double* F, double* Jval, int want_J, DevParams p,
+                            cudaStream_t s) {
+  if (ne == 0) return;
+  SHAKTI_LAUNCH(assemble_atomic_kernel, div_up(ne, 128), 128, 0, s, ne, n_owned, c0, c1, c2, slot, f, kbar,
+                dt, N_bdry, F, Jval, want_J, p);
+}
+
+// F[bc] = N[bc] - g ; J[bc,bc] = 1  (DOLFINx set_bc with scale -1 / insert_diagonal)
+__global__ void apply_bc_kernel(int32_t n_owned, const uint8_t* __restrict__ isbc, const double* __restrict__ N,
+                                double N_bdry, const int32_t* __restrict__ diag_pos, double* __restrict__ F,
+                                double* __restrict__ Jval, int want_J) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_owned || !isbc[i]) return;
+  F[i] = N[i] - N_bdry;
+  if (want_J) Jval[diag_pos[i]] = 1.0;
+}
+void launch_apply_bc(int32_t n_owned, const uint8_t* isbc, const double* N, double N_bdry,
+                     const int32_t* diag_pos, double* F, double* Jval, int want_J, cudaStream_t s) {
+  if (n_owned == 0) return;
+  SHAKTI_LAUNCH(apply_bc_kernel, div_up(n_owned, 256), 256, 0, s, n_owned, isbc, N, N_bdry, diag_pos, F, Jval, want_J);
+}
+
+// ------------------------------------------------------------------ nodal updates
+// Function.interpolate(Expression): the value at vertex i comes from the highest-index cell
+// containing i, evaluated with that cell's constant gradients.
+struct WinGeo {
+  int32_t v[3];
+  int loc;
+  Geo g;
+};
+__device__ __forceinline__ WinGeo win_geometry(const int32_t* __restrict__ win, int32_t i,
+                                               const double* __restrict__ x, const double* __restrict__ y) {
+  WinGeo w;
+  const int4 t = reinterpret_cast<const int4*>(win)[i];
+  w.v[0] = t.x; w.v[1] = t.y; w.v[2] = t.z; w.loc = t.w;
+  if (w.loc >= 0) w.g = geometry(x[t.x], y[t.x], x[t.y], y[t.y], x[t.z], y[t.z]);
+  return w;
+}
+__device__ __forceinline__ void cell_grad(const WinGeo& w, const double f[3], double& gx, double& gy) {
+  gx = f[0] * w.g.gx[0] + f[1] * w.g.gx[1] + f[2] * w.g.gx[2];
+  gy = f[0] * w.g.gy[0] + f[1] * w.g.gy[1] + f[2] * w.g.gy[2];
+}
+
+// q <- -|b|^3 g grad h / (12 nu (1 + omega |q_old|/nu))        (solvers.py:143,186)
+__global__ void __launch_bounds__(256)
+update_q_kernel(int32_t n_owned, const int32_t* __restrict__ win, const double* __restrict__ x,
+                const double* __restrict__ y, const double* __restrict__ h0, const double* __restrict__ N,
+                const double* __restrict__ b, double* __restrict__ qx, double* __restrict__ qy, DevParams p) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_owned) return;
+  const WinGeo w = win_geometry(win, i, x, y);
+  if (w.loc < 0) return;
+  double h[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) h[a] = h0[w.v[a]] - N[w.v[a]] / p.rwg;
+  double ghx, ghy;
+  cell_grad(w, h, ghx, ghy);
+  const double bi = fabs(b[i]);
+  const double qxo = qx[i], qyo = qy[i];
+  const double Re = sqrt(qxo * qxo + qyo * qyo) / p.nu;
+  const double p1 = -(bi * bi * bi) * p.g;
+  const double p2 = 12.0 * p.nu * (1.0 + p.omega * Re);
+  qx[i] = p1 * ghx / p2;
+  qy[i] = p1 * ghy / p2;
+}
+void launch_update_q(int32_t n_owned, const int32_t* win, const double* x, const double* y, const double* h0,
+                     const double* N, const double* b, double* qx, double* qy, DevParams p, cudaStream_t s) {
+  if (n_owned == 0) return;
+  SHAKTI_LAUNCH(update_q_kernel, div_up(n_owned, 256), 256, 0, s, n_owned, win, x, y, h0, N, b, qx, qy, p);
+}
+
+__device__ __forceinline__ double melt_at_vertex(const WinGeo& w, int32_t i, const double* __restrict__ h0,
+                                                 const double* __restrict__ N, const double* __restrict__ b,
+                                                 const double* __restrict__ qx, const double* __restrict__ qy,
+                                                 const double* __restrict__ G, const double* __restrict__ melt,
+                                                 const DevParams& p) {
+  double h[3], bb[3], mm[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    h[a] = h0[w.v[a]] - N[w.v[a]] / p.rwg;
+    bb[a] = b[w.v[a]];
+    mm[a] = melt[w.v[a]];
+  }
+  double ghx, ghy, gbx, gby, gmx, gmy;
+  cell_grad(w, h, ghx, ghy);
+  cell_grad(w, bb, gbx, gby);
+  cell_grad(w, mm, gmx, gmy);
+  const double gb2 = gbx * gbx + gby * gby;
+  const double m0 = (G[i] - p.rwg * (qx[i] * ghx + qy[i] * ghy)) / p.Lh;
+  const double md = (gb2 * melt[i] + b[i] * (gmx * gbx + gmy * gby)) / (1.0 + gb2);
+  return m0 + md;
+}
+
+// melt_n <- Melt(q_new, Head(N_new), G, b_old, melt_old)        (solvers.py:165,189)
+__global__ void __launch_bounds__(256)
+update_melt_kernel(int32_t n_owned, const int32_t* __restrict__ win, const double* __restrict__ x,
+                   const double* __restrict__ y, const double* __restrict__ h0, const double* __restrict__ N,
+                   const double* __restrict__ b, const double* __restrict__ qx, const double* __restrict__ qy,
+                   const double* __restrict__ G, const double* __restrict__ melt_old,
+                   double* __restrict__ melt_new, DevParams p) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_owned) return;
+  const WinGeo w = win_geometry(win, i, x, y);
+  if (w.loc < 0) { melt_new[i] = melt_old[i]; return; }
+  melt_new[i] = melt_at_vertex(w, i, h0, N, b, qx, qy, G, melt_old, p);
+}
+void launch_update_melt(int32_t n_owned, const int32_t* win, const double* x, const double* y, const double* h0,
+                        const double* N, const double* b, const double* qx, const double* qy, const double* G,
+                        const double* melt_old, double* melt_new, DevParams p, cudaStream_t s) {
+  if (n_owned == 0) return;
+  SHAKTI_LAUNCH(update_melt_kernel, div_up(n_owned, 256), 256, 0, s, n_owned, win, x, y, h0, N, b, qx, qy, G,
+                melt_old, melt_new, p);
+}
+
+// b <- max(b + dt (Melt(q_new, N_new, b_old, melt_new)/rho_i - A b N |N|^(n-1)), b_min)
+// (solvers.py:162,192,196)
+__global__ void __launch_bounds__(256)
+update_b_kernel(int32_t n_owned, const int32_t* __restrict__ win, const double* __restrict__ x,
+                const double* __restrict__ y, const double* __restrict__ h0, const double* __restrict__ N,
+                const double* __restrict__ b_old, const double* __restrict__ qx, const double* __restrict__ qy,
+                const double* __restrict__ G, const double* __restrict__ melt, double* __restrict__ b_new,
+                double dt, double b_min, DevParams p) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_owned) return;
+  const WinGeo w = win_geometry(win, i, x, y);
+  double bn;
+  if (w.loc < 0) bn = b_old[i];
+  else {
+    const double m = melt_at_vertex(w, i, h0, N, b_old, qx, qy, G, melt, p);
+    const double Ni = N[i];
+    const double clos = p.A * b_old[i] * Ni * powabs(Ni, p.n - 1.0, p.n_is_3);
+    bn = b_old[i] + dt * (m / p.rho_i - clos);
+  }
+  b_new[i] = bn < b_min ? b_min : bn;
+}
+void launch_update_b(int32_t n_owned, const int32_t* win, const double* x, const double* y, const double* h0,
+                     const double* N, const double* b_old, const double* qx, const double* qy, const double* G,
+                     const double* melt, double* b_new, double dt, double b_min, DevParams p, cudaStream_t s) {
+  if (n_owned == 0) return;
+  SHAKTI_LAUNCH(update_b_kernel, div_up(n_owned, 256), 256, 0, s, n_owned, win, x, y, h0, N, b_old, qx, qy, G,
+                melt, b_new, dt, b_min, p);
+}
+
+// ------------------------------------------------------------------ SELL-32 SpMV family
+// One thread per row, one warp per slice: entry k of the 32 rows of a slice is contiguous, so
+// value/column loads are perfectly coalesced; x is gathered through L1/L2 (rows are Morton
+// ordered, neighbours are close in memory).
+enum { SPMV_SET = 0, SPMV_ADD = 1, SPMV_RESID = 2, SPMV_JACOBI = 3 };
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+spmv_sell_kernel(SellView A, const double* __restrict__ x, const double* __restrict__ b,
+                 const double* __restrict__ dinv, double omega, double* __restrict__ y) {
+  const int32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+  const int32_t slice = row >> 5;
+  if (slice >= A.n_slices) return;
+  const int32_t base = A.slice_ptr[slice];
+  const int32_t w = (A.slice_ptr[slice + 1] - base) >> 5;
+  const int32_t* __restrict__ cp = A.col + base + (row & 31);
+  const double* __restrict__ vp = A.val + base + (row & 31);
+  double acc = 0.0;
+#pragma unroll 4
+  for (int k = 0; k < w; ++k) acc += vp[32 * k] * x[cp[32 * k]];
+  if (row >= A.n_rows) return;
+  if (MODE == SPMV_SET) y[row] = acc;
+  else if (MODE == SPMV_ADD) y[row] += acc;
+  else if (MODE == SPMV_RESID) y[row] = b[row] - acc;
+  else y[row] = x[row] + omega * dinv[row] * (b[row] - acc);
+}
+
+template <int MODE>
+static void spmv_launch(SellView A, const double* x, const double* b, const double* dinv, double omega,
+                        double* y, cudaStream_t s) {
+  if (A.n_rows == 0) return;
+  const int64_t threads = (int64_t)A.n_slices * 32;
+  SHAKTI_LAUNCH(spmv_sell_kernel<MODE>, div_up(threads, 256), 256, 0, s, A, x, b, dinv, omega, y);
+}
+void launch_spmv(SellView A, const double* x, double* y, cudaStream_t s) { spmv_launch<SPMV_SET>(A, x, nullptr, nullptr, 0, y, s); }
+void launch_spmv_add(SellView A, const double* x, double* y, cudaStream_t s) { spmv_launch<SPMV_ADD>(A, x, nullptr, nullptr, 0, y, s); }
+void launch_residual(SellView A, const double* x, const double* b, double* r, cudaStream_t s) { spmv_launch<SPMV_RESID>(A, x, b, nullptr, 0, r, s); }
+void launch_jacobi(SellView A, const double* dinv, const double* b, const double* x, double* x_out, double omega,
+                   cudaStream_t s) { spmv_launch<SPMV_JACOBI>(A, x, b, dinv, omega, x_out, s); }
+
+__global__ void extract_dinv_kernel(int32_t n, const int32_t* __restrict__ diag_pos, const double* __restrict__ val,
+                                    double* __restrict__ dinv) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double d = val[diag_pos[i]];
+  dinv[i] = d != 0.0 ? 1.0 / d : 1.0;
+}
+void launch_extract_dinv(int32_t n, const int32_t* diag_pos, const double* val, double* dinv, cudaStream_t s) {
+  if (n == 0) return;
+  SHAKTI_LAUNCH(extract_dinv_kernel, div_up(n, 256), 256, 0, s, n, diag_pos, val, dinv);
+}
+
+// ------------------------------------------------------------------ reductions
+constexpr int kRedThreads = 256;
+
+void Reducer::init(int sm_count) {
+  max_blocks = sm_count * 8;
+  partial.alloc((size_t)max_blocks * 8);
+  counter.alloc_zero(1);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// out[k] = sum_i V[k*ld + i] * w[i], k < NV.  Two stages in one launch: per-block partials,
+// then the last block to finish sums them in a fixed order (deterministic result).
+template <int NV>
+__global__ void __launch_bounds__(kRedThreads)
+multi_dot_kernel(int64_t n, const double* __restrict__ V, int64_t ld, const double* __restrict__ w,
+                 double* __restrict__ partial, unsigned int* __restrict__ counter, double* __restrict__ out) {
+  double acc[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double wi = w[i];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc[k] += V[k * ld + i] * wi;
+  }
+  __shared__ double sm[NV][kRedThreads / 32];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const double v = warp_sum(acc[k]);
+    if (lane == 0) sm[k][wid] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double v = 0.0;
+#pragma unroll
+    for (int j = 0; j < kRedThreads / 32; ++j) v += sm[threadIdx.x][j];
+    partial[(size_t)blockIdx.x * NV + threadIdx.x] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  for (int k = wid; k < NV; k += kRedThreads / 32) {
+    double v = 0.0;
+    for (int b = lane; b < (int)gridDim.x; b += 32) v += partial[(size_t)b * NV + k];
+    v = warp_sum(v);
+    if (lane == 0) out[k] = v;
+  }
+  if (threadIdx.x == 0) *counter = 0u;
+}
+
+void launch_multi_dot(Reducer& red, int64_t n, int nvec, const double* V, int64_t ld, const double* w,
+                      double* out, cudaStream_t s) {
+  int blocks = (int)std::min<int64_t>(red.max_blocks, std::max<int64_t>(1, (n + kRedThreads * 4 - 1) / (kRedThreads * 4)));
+  int done = 0;
+  while (done < nvec) {
+    const int c = std::min(8, nvec - done);
+    const double* Vc = V + (int64_t)done * ld;
+    double* oc = out + done;
+    switch (c) {
+      case 1: SHAKTI_LAUNCH(multi_dot_kernel<1>, blocks, kRedThreads, 0, s, n, Vc, ld, w, red.partial.p, red.counter.p, oc); break;
+      case 2: SHAKTI_LAUNCH(multi_dot_kernel<2>, blocks, kRedThreads, 0, s, n, Vc, ld, w, red.partial.p, red.counter.p, oc); break;
+      case 3: SHAKTI_LAUNCH(multi_dot_kernel<3>, blocks, kRedThreads, 0, s, n, Vc, ld, w, red.partial.p, red.counter.p, oc); break;
+      case 4: SHAKTI_LAUNCH(multi_dot_kernel<4>, blocks, kRedThreads, 0, s, n, Vc, ld, w, red.partial.p, red.counter.p, oc); break;
+      case 5: SHAKTI_LAUNCH(multi_dot_kernel<5>, blocks, kRedThreads, 0, s, n, Vc, ld, w, red.partial.p, red.counter.p, oc); break;
+      case 6: SHAKTI_LAUNCH(multi_dot_kernel<6>, blocks, kRedThreads, 0, s, n, Vc, ld, w, red.partial.p, red.counter.p, oc); break;
+      case 7: SHAKTI_LAUNCH(multi_dot_kernel<7>, blocks, kRedThreads, 0, s, n, Vc, ld, w, red.partial.p, red.counter.p, oc); break;
+      default: SHAKTI_LAUNCH(multi_dot_kernel<8>, blocks, kRedThreads, 0, s, n, Vc, ld, w, red.partial.p, red.counter.p, oc); break;
+    }
+    done += c;
+  }
+}
+
+// w -= sum_k h[k] V_k  (SUB) or y = sum_k h[k] V_k (SET, first chunk) / y += ... (ADD)
+enum { COMB_SUB = 0, COMB_SET = 1, COMB_ADD = 2 };
+template <int NV, int MODE>
+__global__ void __launch_bounds__(256)
+combine_kernel(int64_t n, const double* __restrict__ V, int64_t ld, const double* __restrict__ h,
+               double* __restrict__ w) {
+  double hk[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) hk[k] = h[k];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc += hk[k] * V[k * ld + i];
+    if (MODE == COMB_SUB) w[i] -= acc;
+    else if (MODE == COMB_SET) w[i] = acc;
+    else w[i] += acc;
+  }
+}
+
+template <int MODE>
+static void combine_chunk(int c, int blocks, int64_t n, const double* V, int64_t ld, const double* h, double* w,
+                          cudaStream_t s) {
+  switch (c) {
+    case 1: SHAKTI_LAUNCH((combine_kernel<1, MODE>), blocks, 256, 0, s, n, V, ld, h, w); break;
+    case 2: SHAKTI_LAUNCH((combine_kernel<2, MODE>), blocks, 256, 0, s, n, V, ld, h, w); break;
+    case 3: SHAKTI_LAUNCH((combine_kernel<3, MODE>), blocks, 256, 0, s, n, V, ld, h, w); break;
+    case 4: SHAKTI_LAUNCH((combine_kernel<4, MODE>), blocks, 256, 0, s, n, V, ld, h, w); break;
+    case 5: SHAKTI_LAUNCH((combine_kernel<5, MODE>), blocks, 256, 0, s, n, V, ld, h, w); break;
+    case 6: SHAKTI_LAUNCH((combine_kernel<6, MODE>), blocks, 256, 0, s, n, V, ld, h, w); break;
+    case 7: SHAKTI_LAUNCH((combine_kernel<7, MODE>), blocks, 256, 0, s, n, V, ld, h, w); break;
+    default: SHAKTI_LAUNCH((combine_kernel<8, MODE>), blocks, 256, 0, s, n, V, ld, h, w); break;
+  }
+}
+static int stream_blocks(int64_t n) { return (int)std::min<int64_t>(148 * 16, std::max<int64_t>(1, (n + 255) / 256)); }
+
+void launch_multi_axpy_neg(int64_t n, int nvec, const double* V, int64_t ld, const double* h, double* w,
+                           cudaStream_t s) {
+  if (n == 0) return;
+  for (int done = 0; done < nvec; done += 8)
+    combine_chunk<COMB_SUB>(std::min(8, nvec - done), stream_blocks(n), n, V + (int64_t)done * ld, ld, h + done, w, s);
+}
+void launch_combine(int64_t n, int nvec, const double* V, int64_t ld, const double* h, double* y, cudaStream_t s) {
+  if (n == 0) return;
+  for (int done = 0; done < nvec; done += 8) {
+    const int c = std::min(8, nvec - done);
+    if (done == 0) combine_chunk<COMB_SET>(c, stream_blocks(n), n, V, ld, h, y, s);
+    else combine_chunk<COMB_ADD>(c, stream_blocks(n), n, V + (int64_t)done * ld, ld, h + done, y, s);
+  }
+}
+
+// ------------------------------------------------------------------ streaming vector kernels
+// (x, y without __restrict__: called in place)
+__global__ void scale_dev_kernel(int64_t n, const double* x, const double* __restrict__ alpha, int reciprocal,
+                                 double* y) {
+  const double a = reciprocal ? 1.0 / alpha[0] : alpha[0];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = a * x[i];
+}
+void launch_scale_dev(int64_t n, const double* x, const double* alpha_dev, int reciprocal, double* y, cudaStream_t s) {
+  if (n == 0) return;
+  SHAKTI_LAUNCH(scale_dev_kernel, stream_blocks(n), 256, 0, s, n, x, alpha_dev, reciprocal, y);
+}
+__global__ void axpy_kernel(int64_t n, double alpha, const double* __restrict__ x, double* __restrict__ y) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] += alpha * x[i];
+}
+void launch_axpy(int64_t n, double alpha, const double* x, double* y, cudaStream_t s) {
+  if (n == 0) return;
+  SHAKTI_LAUNCH(axpy_kernel, stream_blocks(n), 256, 0, s, n, alpha, x, y);
+}
+// out = mask ? 0 : a
+__global__ void xmy_masked_kernel(int64_t n, const double* __restrict__ a, const uint8_t* __restrict__ mask,
+                                  double* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = mask[i] ? 0.0 : a[i];
+}
+void launch_xmy_masked(int64_t n, const double* a, const uint8_t* mask, double* out, cudaStream_t s) {
+  if (n == 0) return;
+  SHAKTI_LAUNCH(xmy_masked_kernel, stream_blocks(n), 256, 0, s, n, a, mask, out);
+}
+__global__ void pointwise_mul_kernel(int64_t n, const double* __restrict__ a, const double* __restrict__ b,
+                                     double scale, double* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = scale * a[i] * b[i];
+}
+void launch_pointwise_mul(int64_t n, const double* a, const double* b, double scale, double* out, cudaStream_t s) {
+  if (n == 0) return;
+  SHAKTI_LAUNCH(pointwise_mul_kernel, stream_blocks(n), 256, 0, s, n, a, b, scale, out);
+}
+__global__ void fill_kernel(int64_t n, double v, double* __restrict__ x) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] = v;
+}
+void launch_fill(int64_t n, double v, double* x, cudaStream_t s) {
+  if (n == 0) return;
+  SHAKTI_LAUNCH(fill_kernel, stream_blocks(n), 256, 0, s, n, v, x);
+}
+__global__ void gather_kernel(int64_t n, const int32_t* __restrict__ idx, const double* __restrict__ src,
+                              double* __restrict__ dst) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[idx[i]];
+}
+void launch_gather(int64_t n, const int32_t* idx, const double* src, double* dst, cudaStream_t s) {
+  if (n == 0) return;
+  SHAKTI_LAUNCH(gather_kernel, stream_blocks(n), 256, 0, s, n, idx, src, dst);
+}
+__global__ void scatter_kernel(int64_t n, const int32_t* __restrict__ idx, const double* __restrict__ src,
+                               double* __restrict__ dst) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[idx[i]] = src[i];
+}
+void launch_scatter(int64_t n, const int32_t* idx, const double* src, double* dst, cudaStream_t s) {
+  if (n == 0) return;
+  SHAKTI_LAUNCH(scatter_kernel, stream_blocks(n), 256, 0, s, n, idx, src, dst);
+}
+// static part of Head (constitutive.py:6-9): h0 = z_b + (rho_i/rho_w)(z_s - z_b)
+__global__ void head0_kernel(int64_t n, const double* __restrict__ z_b, const double* __restrict__ z_s, double ratio,
+                             double* __restrict__ h0) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    h0[i] = z_b[i] + ratio * (z_s[i] - z_b[i]);
+}
+void launch_head0(int64_t n, const double* z_b, const double* z_s, double ratio, double* h0, cudaStream_t s) {
+  if (n == 0) return;
+  SHAKTI_LAUNCH(head0_kernel, stream_blocks(n), 256, 0, s, n, z_b, z_s, ratio, h0);
+}
+__global__ void interleave_kernel(int64_t n, const double* __restrict__ a, const double* __restrict__ b,
+                                  double* __restrict__ ab) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    ab[2 * i] = a[i];
+    ab[2 * i + 1] = b[i];
+  }
+}
+void launch_interleave(int64_t n, const double* a, const double* b, double* ab, cudaStream_t s) {
+  if (n == 0) return;
+  SHAKTI_LAUNCH(interleave_kernel, stream_blocks(n), 256, 0, s, n, a, b, ab);
+}
+__global__ void deinterleave_kernel(int64_t n, const double* __restrict__ ab, double* __restrict__ a,
+                                    double* __restrict__ b) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    a[i] = ab[2 * i];
+    b[i] = ab[2 * i + 1];
+  }
+}
+void launch_deinterleave(int64_t n, const double* ab, double* a, double* b, cudaStream_t s) {
+  if (n == 0) return;
+  SHAKTI_LAUNCH(deinterleave_kernel, stream_blocks(n), 256, 0, s, n, ab, a, b);
+}
+
+}  // namespace shakti

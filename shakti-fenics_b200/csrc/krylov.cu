@@ -1,0 +1,234 @@
+// GMRES(m) / BiCGStab on the device (see krylov.h).
+#include "krylov.h"
+
+#include <cmath>
+
+namespace shakti {
+
+// ------------------------------------------------------------------ small device-side state
+__global__ void gmres_begin_kernel(int m, double* g, double* scal) {
+  // scal[0] = <r,r> on entry
+  const double beta = sqrt(fmax(scal[0], 0.0));
+  for (int i = 0; i <= m; ++i) g[i] = 0.0;
+  g[0] = beta;
+  scal[1] = beta;
+}
+
+// Column j of the Hessenberg matrix: combine the two Gram-Schmidt passes, take the norm of the
+// new direction from <w,w> of pass two (Pythagoras on the tiny second correction), apply the
+// stored Givens rotations, create the new one, update the residual estimate.
+__global__ void gmres_update_kernel(int j, int m, const double* h, const double* h2, double* H, double* cs,
+                                    double* sn, double* g, double* scal) {
+  double* col = H + (size_t)j * (m + 1);
+  double corr = 0.0;
+  for (int i = 0; i <= j; ++i) {
+    col[i] = h[i] + h2[i];
+    corr += h2[i] * h2[i];
+  }
+  const double ww = h2[j + 1];
+  const double hj1 = sqrt(fmax(ww - corr, 0.0));
+  col[j + 1] = hj1;
+  for (int i = 0; i < j; ++i) {
+    const double t = cs[i] * col[i] + sn[i] * col[i + 1];
+    col[i + 1] = -sn[i] * col[i] + cs[i] * col[i + 1];
+    col[i] = t;
+  }
+  const double d = hypot(col[j], col[j + 1]);
+  const double c = d > 0 ? col[j] / d : 1.0, s = d > 0 ? col[j + 1] / d : 0.0;
+  cs[j] = c;
+  sn[j] = s;
+  col[j] = d;
+  col[j + 1] = 0.0;
+  g[j + 1] = -s * g[j];
+  g[j] = c * g[j];
+  scal[2] = hj1;
+  scal[3] = fabs(g[j + 1]);
+}
+
+__global__ void gmres_solve_y_kernel(int k, int m, const double* H, const double* g, double* y) {
+  for (int i = k - 1; i >= 0; --i) {
+    double s = g[i];
+    for (int l = i + 1; l < k; ++l) s -= H[(size_t)l * (m + 1) + i] * y[l];
+    const double d = H[(size_t)i * (m + 1) + i];
+    y[i] = d != 0.0 ? s / d : 0.0;
+  }
+}
+
+__global__ void sub_kernel(int64_t n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = a[i] - b[i];
+}
+// y = a*x + b*y, out-of-place capable: out = a*x + b*y
+// (no __restrict__: called in place)
+__global__ void axpby_kernel(int64_t n, double a, const double* x, double b, const double* y, double* out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = a * x[i] + b * y[i];
+}
+static int sblocks(int64_t n) { return (int)std::min<int64_t>(148 * 16, std::max<int64_t>(1, (n + 255) / 256)); }
+
+// ------------------------------------------------------------------ GMRES
+void Gmres::init(int64_t n_owned, int64_t n_local, int restart, int sm_count, cudaStream_t s) {
+  n_ = n_owned; nl_ = n_local; m_ = restart; s_ = s;
+  ld_ = ((n_owned + 31) / 32) * 32;
+  if (ld_ == 0) ld_ = 32;
+  V_.alloc_zero((size_t)(m_ + 1) * ld_, s);
+  z_.alloc_zero(std::max<int64_t>(n_local, 1), s);
+  u_.alloc_zero(ld_, s);
+  r_.alloc_zero(ld_, s);
+  const size_t ns = (size_t)(m_ + 2) * 2 + (size_t)(m_ + 1) * m_ + 2 * m_ + (m_ + 1) + m_ + 4;
+  small_.alloc_zero(ns, s);
+  double* p = small_.p;
+  h_ = p; p += m_ + 2;
+  h2_ = p; p += m_ + 2;
+  H_ = p; p += (size_t)(m_ + 1) * m_;
+  cs_ = p; p += m_;
+  sn_ = p; p += m_;
+  g_ = p; p += m_ + 1;
+  y_ = p; p += m_;
+  scal_ = p;
+  red_.init(sm_count);
+  if (!host_status_) SHAKTI_CUDA(cudaMallocHost(&host_status_, 4 * sizeof(double)));
+}
+
+Gmres::~Gmres() {
+  if (host_status_) cudaFreeHost(host_status_);
+}
+
+KrylovResult Gmres::solve(const ApplyFn& A, const PrecFn& M, const AllReduceFn& allreduce, const double* b,
+                          double* x, double rtol, double atol, int max_it) {
+  KrylovResult res;
+  launch_fill(n_, 0.0, x, s_);
+  SHAKTI_CUDA(cudaMemcpyAsync(r_.p, b, n_ * sizeof(double), cudaMemcpyDeviceToDevice, s_));
+  double bnorm = -1.0, tol = 0.0;
+  int total = 0;
+  for (;;) {
+    launch_multi_dot(red_, n_, 1, r_.p, ld_, r_.p, scal_, s_);
+    allreduce(scal_, 1);
+    SHAKTI_LAUNCH(gmres_begin_kernel, 1, 1, 0, s_, m_, g_, scal_);
+    SHAKTI_CUDA(cudaMemcpyAsync(host_status_, scal_, 4 * sizeof(double), cudaMemcpyDeviceToHost, s_));
+    SHAKTI_CUDA(cudaStreamSynchronize(s_));
+    const double beta = host_status_[1];
+    if (bnorm < 0) {
+      bnorm = beta;
+      tol = std::max(rtol * bnorm, atol);
+    }
+    double resid = beta;
+    if (!(beta > tol) || !std::isfinite(beta)) {
+      res.converged = std::isfinite(beta);
+      res.relres = bnorm > 0 ? beta / bnorm : 0.0;
+      break;
+    }
+    launch_scale_dev(n_, r_.p, scal_ + 1, 1, V_.p, s_);
+    int k = 0;
+    bool done = false;
+    for (int j = 0; j < m_; ++j) {
+      double* w = V_.p + (size_t)(j + 1) * ld_;
+      M(V_.p + (size_t)j * ld_, z_.p);
+      A(z_.p, w);
+      launch_multi_dot(red_, n_, j + 1, V_.p, ld_, w, h_, s_);
+      allreduce(h_, j + 1);
+      launch_multi_axpy_neg(n_, j + 1, V_.p, ld_, h_, w, s_);
+      launch_multi_dot(red_, n_, j + 2, V_.p, ld_, w, h2_, s_);
+      allreduce(h2_, j + 2);
+      launch_multi_axpy_neg(n_, j + 1, V_.p, ld_, h2_, w, s_);
+      SHAKTI_LAUNCH(gmres_update_kernel, 1, 1, 0, s_, j, m_, h_, h2_, H_, cs_, sn_, g_, scal_);
+      SHAKTI_CUDA(cudaMemcpyAsync(host_status_, scal_, 4 * sizeof(double), cudaMemcpyDeviceToHost, s_));
+      SHAKTI_CUDA(cudaStreamSynchronize(s_));
+      ++total;
+      k = j + 1;
+      const double hj1 = host_status_[2];
+      resid = host_status_[3];
+      if (!std::isfinite(resid)) { done = true; break; }
+      if (resid <= tol || total >= max_it || !(hj1 > 1e-300 * (1.0 + beta))) { done = true; break; }
+      launch_scale_dev(n_, w, scal_ + 2, 1, w, s_);
+    }
+    SHAKTI_LAUNCH(gmres_solve_y_kernel, 1, 1, 0, s_, k, m_, H_, g_, y_);
+    launch_combine(n_, k, V_.p, ld_, y_, u_.p, s_);
+    M(u_.p, z_.p);
+    launch_axpy(n_, 1.0, z_.p, x, s_);
+    res.relres = bnorm > 0 ? resid / bnorm : 0.0;
+    if (done && (resid <= tol || !std::isfinite(resid))) {
+      res.converged = std::isfinite(resid);
+      break;
+    }
+    if (total >= max_it) break;
+    // restart: r = b - A x
+    SHAKTI_CUDA(cudaMemcpyAsync(z_.p, x, n_ * sizeof(double), cudaMemcpyDeviceToDevice, s_));
+    A(z_.p, u_.p);
+    SHAKTI_LAUNCH(sub_kernel, sblocks(n_), 256, 0, s_, n_, b, u_.p, r_.p);
+  }
+  res.iterations = total;
+  return res;
+}
+
+// ------------------------------------------------------------------ BiCGStab (right preconditioned)
+void BiCgStab::init(int64_t n_owned, int64_t n_local, int sm_count, cudaStream_t s) {
+  n_ = n_owned; nl_ = n_local; s_ = s;
+  const size_t n1 = std::max<int64_t>(n_owned, 1), nl = std::max<int64_t>(n_local, 1);
+  r_.alloc_zero(n1, s); r0_.alloc_zero(n1, s); p_.alloc_zero(n1, s); v_.alloc_zero(n1, s);
+  s_v_.alloc_zero(n1, s); t_.alloc_zero(n1, s); ph_.alloc_zero(nl, s); sh_.alloc_zero(nl, s);
+  dots_.alloc_zero(8, s);
+  red_.init(sm_count);
+  if (!host_) SHAKTI_CUDA(cudaMallocHost(&host_, 8 * sizeof(double)));
+}
+BiCgStab::~BiCgStab() {
+  if (host_) cudaFreeHost(host_);
+}
+
+KrylovResult BiCgStab::solve(const ApplyFn& A, const PrecFn& M, const AllReduceFn& allreduce, const double* b,
+                             double* x, double rtol, double atol, int max_it) {
+  KrylovResult res;
+  auto dot = [&](const double* a, const double* c) {
+    launch_multi_dot(red_, n_, 1, a, n_, c, dots_.p, s_);
+    allreduce(dots_.p, 1);
+    SHAKTI_CUDA(cudaMemcpyAsync(host_, dots_.p, sizeof(double), cudaMemcpyDeviceToHost, s_));
+    SHAKTI_CUDA(cudaStreamSynchronize(s_));
+    return host_[0];
+  };
+  auto axpby = [&](double a, const double* xx, double bb, const double* yy, double* out) {
+    SHAKTI_LAUNCH(axpby_kernel, sblocks(n_), 256, 0, s_, n_, a, xx, bb, yy, out);
+  };
+  launch_fill(n_, 0.0, x, s_);
+  SHAKTI_CUDA(cudaMemcpyAsync(r_.p, b, n_ * sizeof(double), cudaMemcpyDeviceToDevice, s_));
+  SHAKTI_CUDA(cudaMemcpyAsync(r0_.p, b, n_ * sizeof(double), cudaMemcpyDeviceToDevice, s_));
+  launch_fill(n_, 0.0, p_.p, s_);
+  launch_fill(n_, 0.0, v_.p, s_);
+  const double bnorm = std::sqrt(std::max(dot(r_.p, r_.p), 0.0));
+  const double tol = std::max(rtol * bnorm, atol);
+  double rho = 1, alpha = 1, omega = 1, resid = bnorm;
+  if (!(bnorm > tol)) { res.converged = true; return res; }
+  int it = 0;
+  while (it < max_it) {
+    const double rho_new = dot(r0_.p, r_.p);
+    if (rho_new == 0.0 || !std::isfinite(rho_new)) break;
+    const double beta = (rho_new / rho) * (alpha / omega);
+    axpby(1.0, p_.p, -omega, v_.p, p_.p);   // p = p - omega v
+    axpby(1.0, r_.p, beta, p_.p, p_.p);     // p = r + beta p
+    M(p_.p, ph_.p);
+    A(ph_.p, v_.p);
+    const double r0v = dot(r0_.p, v_.p);
+    if (r0v == 0.0 || !std::isfinite(r0v)) break;
+    alpha = rho_new / r0v;
+    axpby(1.0, r_.p, -alpha, v_.p, s_v_.p);  // s = r - alpha v
+    launch_axpy(n_, alpha, ph_.p, x, s_);
+    ++it;
+    resid = std::sqrt(std::max(dot(s_v_.p, s_v_.p), 0.0));
+    if (resid <= tol) { res.converged = true; break; }
+    M(s_v_.p, sh_.p);
+    A(sh_.p, t_.p);
+    const double tt = dot(t_.p, t_.p), ts = dot(t_.p, s_v_.p);
+    if (tt == 0.0 || !std::isfinite(tt)) break;
+    omega = ts / tt;
+    launch_axpy(n_, omega, sh_.p, x, s_);
+    axpby(1.0, s_v_.p, -omega, t_.p, r_.p);  // r = s - omega t
+    resid = std::sqrt(std::max(dot(r_.p, r_.p), 0.0));
+    if (resid <= tol) { res.converged = true; break; }
+    if (omega == 0.0) break;
+    rho = rho_new;
+  }
+  res.iterations = it;
+  res.relres = bnorm > 0 ? resid / bnorm : 0.0;
+  return res;
+}
+
+}  // namespace shakti

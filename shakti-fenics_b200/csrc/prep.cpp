@@ -1,0 +1,363 @@
+// Host-side mesh preprocessing (see prep.h).
+#include "prep.h"
+
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+#include <stdexcept>
+
+namespace shakti {
+
+// ------------------------------------------------------------------ generic sparse helpers
+
+HostSell sell_from_csr(const HostCsr& a) {
+  HostSell s;
+  s.n_rows = a.n_rows;
+  s.n_cols = a.n_cols;
+  s.n_slices = (a.n_rows + 31) / 32;
+  s.slice_ptr.assign(s.n_slices + 1, 0);
+  s.rowlen.resize(a.n_rows);
+  for (int64_t r = 0; r < a.n_rows; ++r) s.rowlen[r] = a.rowptr[r + 1] - a.rowptr[r];
+  int64_t off = 0;
+  for (int64_t sl = 0; sl < s.n_slices; ++sl) {
+    int w = 0;
+    for (int64_t r = sl * 32; r < std::min<int64_t>(a.n_rows, sl * 32 + 32); ++r) w = std::max(w, s.rowlen[r]);
+    s.slice_ptr[sl] = (int32_t)off;
+    off += 32 * (int64_t)w;
+    if (off > 2000000000LL) throw std::runtime_error("SELL matrix too large for int32 offsets");
+  }
+  s.slice_ptr[s.n_slices] = (int32_t)off;
+  s.col.resize(off);
+  for (int64_t sl = 0; sl < s.n_slices; ++sl) {
+    int w = (s.slice_ptr[sl + 1] - s.slice_ptr[sl]) / 32;
+    for (int lane = 0; lane < 32; ++lane) {
+      int64_t r = sl * 32 + lane;
+      int32_t padcol = (int32_t)std::min<int64_t>(std::min<int64_t>(r, a.n_rows - 1), a.n_cols - 1);
+      if (padcol < 0) padcol = 0;
+      for (int k = 0; k < w; ++k) {
+        int64_t p = (int64_t)s.slice_ptr[sl] + 32 * (int64_t)k + lane;
+        if (r < a.n_rows && k < s.rowlen[r]) s.col[p] = a.col[a.rowptr[r] + k];
+        else s.col[p] = padcol;
+      }
+    }
+  }
+  return s;
+}
+
+std::vector<int32_t> sell_positions(const HostCsr& a, const HostSell& s) {
+  std::vector<int32_t> pos(a.nnz());
+  for (int64_t r = 0; r < a.n_rows; ++r)
+    for (int32_t k = a.rowptr[r]; k < a.rowptr[r + 1]; ++k) pos[k] = (int32_t)s.pos(r, k - a.rowptr[r]);
+  return pos;
+}
+
+HostCsr csr_transpose(const HostCsr& a, std::vector<int32_t>* entry_map) {
+  HostCsr t;
+  t.n_rows = a.n_cols;
+  t.n_cols = a.n_rows;
+  t.rowptr.assign(t.n_rows + 1, 0);
+  for (int32_t c : a.col) t.rowptr[c + 1]++;
+  for (int64_t i = 0; i < t.n_rows; ++i) t.rowptr[i + 1] += t.rowptr[i];
+  t.col.resize(a.nnz());
+  if (entry_map) entry_map->resize(a.nnz());
+  std::vector<int32_t> fill(t.rowptr.begin(), t.rowptr.end() - 1);
+  for (int64_t r = 0; r < a.n_rows; ++r)
+    for (int32_t k = a.rowptr[r]; k < a.rowptr[r + 1]; ++k) {
+      int32_t p = fill[a.col[k]]++;
+      t.col[p] = (int32_t)r;  // rows visited ascending => columns of t sorted
+      if (entry_map) (*entry_map)[p] = k;
+    }
+  return t;
+}
+
+// adjacency (incl. diagonal) of rows [0,n_rows) given cells in some numbering; a row is
+// built only if row_of(vertex) >= 0.
+template <class RowOf>
+static HostCsr adjacency(int64_t n_rows, int64_t n_cols, int64_t ne, const int32_t* cells, RowOf row_of) {
+  HostCsr a;
+  a.n_rows = n_rows;
+  a.n_cols = n_cols;
+  std::vector<int32_t> cnt(n_rows + 1, 0);
+  for (int64_t e = 0; e < ne; ++e)
+    for (int i = 0; i < 3; ++i) {
+      int64_t r = row_of(cells[3 * e + i]);
+      if (r >= 0) cnt[r + 1] += 2;
+    }
+  for (int64_t r = 0; r < n_rows; ++r) cnt[r + 1] += 1;  // diagonal
+  std::vector<int64_t> ptr(n_rows + 1, 0);
+  for (int64_t r = 0; r < n_rows; ++r) ptr[r + 1] = ptr[r] + cnt[r + 1];
+  std::vector<int32_t> tmp(ptr[n_rows]);
+  std::vector<int64_t> fill(ptr.begin(), ptr.end() - 1);
+  for (int64_t e = 0; e < ne; ++e)
+    for (int i = 0; i < 3; ++i) {
+      int32_t v = cells[3 * e + i];
+      int64_t r = row_of(v);
+      if (r < 0) continue;
+      tmp[fill[r]++] = cells[3 * e + (i + 1) % 3];
+      tmp[fill[r]++] = cells[3 * e + (i + 2) % 3];
+    }
+  a.rowptr.assign(n_rows + 1, 0);
+  // first pass: sort/unique in place, record lengths
+  std::vector<int32_t> len(n_rows);
+  for (int64_t r = 0; r < n_rows; ++r) {
+    int32_t* b = tmp.data() + ptr[r];
+    int32_t* e = tmp.data() + fill[r];
+    *e++ = -1;  // placeholder for the diagonal, patched by the caller via diag_of
+    len[r] = (int32_t)(e - b);
+  }
+  // the diagonal column id equals the vertex id whose row this is; recover it from cells
+  // by letting the caller supply it: rows are indexed so that row r <-> some vertex id.
+  // To stay generic we rebuild: mark diag after we know it (see wrappers below).
+  a.col.swap(tmp);
+  a.rowptr.resize(n_rows + 1);
+  // stash ptr/len in rowptr temporarily (64-bit safe for our sizes < 2^31)
+  for (int64_t r = 0; r <= n_rows; ++r) a.rowptr[r] = (int32_t)ptr[r];
+  (void)len;
+  return a;
+}
+
+// finish: replace the trailing -1 of each row by diag id, sort, unique, compact
+static void finish_rows(HostCsr& a, const std::vector<int32_t>& diag_id) {
+  int64_t n = a.n_rows;
+  std::vector<int32_t> newptr(n + 1, 0);
+  int64_t w = 0;
+  for (int64_t r = 0; r < n; ++r) {
+    int32_t* b = a.col.data() + a.rowptr[r];
+    int32_t* e = a.col.data() + a.rowptr[r + 1];
+    *(e - 1) = diag_id[r];
+    std::sort(b, e);
+    e = std::unique(b, e);
+    newptr[r] = (int32_t)w;
+    for (int32_t* p = b; p < e; ++p) a.col[w++] = *p;  // w <= position of b, safe in place
+  }
+  newptr[n] = (int32_t)w;
+  a.col.resize(w);
+  a.col.shrink_to_fit();
+  a.rowptr.swap(newptr);
+}
+
+HostCsr caller_csr(int64_t nv, int64_t ne, const int32_t* cells) {
+  HostCsr a = adjacency(nv, nv, ne, cells, [](int32_t v) { return (int64_t)v; });
+  std::vector<int32_t> diag(nv);
+  std::iota(diag.begin(), diag.end(), 0);
+  finish_rows(a, diag);
+  return a;
+}
+
+std::vector<int32_t> locate_dirichlet_dofs(int64_t nv, int64_t ne, const int32_t* cells,
+                                           const uint8_t* marker) {
+  // count incident cells per undirected edge (i<j) at the CSR position (i,j)
+  HostCsr a = caller_csr(nv, ne, cells);
+  std::vector<uint8_t> cnt(a.nnz(), 0);
+  auto find = [&](int32_t i, int32_t j) {
+    const int32_t* b = a.col.data() + a.rowptr[i];
+    const int32_t* e = a.col.data() + a.rowptr[i + 1];
+    return (int64_t)(std::lower_bound(b, e, j) - a.col.data());
+  };
+  for (int64_t c = 0; c < ne; ++c)
+    for (int i = 0; i < 3; ++i) {
+      int32_t u = cells[3 * c + i], v = cells[3 * c + (i + 1) % 3];
+      if (u > v) std::swap(u, v);
+      int64_t p = find(u, v);
+      if (cnt[p] < 255) cnt[p]++;
+    }
+  std::vector<uint8_t> is(nv, 0);
+  for (int64_t i = 0; i < nv; ++i)
+    for (int32_t k = a.rowptr[i]; k < a.rowptr[i + 1]; ++k) {
+      int32_t j = a.col[k];
+      if (j > i && cnt[k] == 1 && marker[i] && marker[j]) is[i] = is[j] = 1;
+    }
+  std::vector<int32_t> out;
+  for (int64_t i = 0; i < nv; ++i)
+    if (is[i]) out.push_back((int32_t)i);
+  return out;
+}
+
+// ------------------------------------------------------------------ Morton ordering
+
+static inline uint64_t spread_bits(uint64_t v) {  // 21 bits -> every 2nd bit
+  v &= 0x1fffff;
+  v = (v | (v << 16)) & 0x0000ffff0000ffffULL;
+  v = (v | (v << 8)) & 0x00ff00ff00ff00ffULL;
+  v = (v | (v << 4)) & 0x0f0f0f0f0f0f0f0fULL;
+  v = (v | (v << 2)) & 0x3333333333333333ULL;
+  v = (v | (v << 1)) & 0x5555555555555555ULL;
+  return v;
+}
+
+static std::vector<int32_t> morton_order(int64_t nv, const double* xy) {
+  double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
+  for (int64_t i = 0; i < nv; ++i) {
+    xmin = std::min(xmin, xy[2 * i]); xmax = std::max(xmax, xy[2 * i]);
+    ymin = std::min(ymin, xy[2 * i + 1]); ymax = std::max(ymax, xy[2 * i + 1]);
+  }
+  // one common scale so that tiles are square in physical space
+  double ext = std::max(xmax - xmin, ymax - ymin);
+  if (!(ext > 0)) ext = 1.0;
+  const double scale = (double)((1 << 20) - 1) / ext;
+  std::vector<std::pair<uint64_t, int32_t>> key(nv);
+  for (int64_t i = 0; i < nv; ++i) {
+    uint64_t qx = (uint64_t)((xy[2 * i] - xmin) * scale);
+    uint64_t qy = (uint64_t)((xy[2 * i + 1] - ymin) * scale);
+    key[i] = {spread_bits(qx) | (spread_bits(qy) << 1), (int32_t)i};
+  }
+  std::sort(key.begin(), key.end());
+  std::vector<int32_t> order(nv);
+  for (int64_t i = 0; i < nv; ++i) order[i] = key[i].second;
+  return order;
+}
+
+// ------------------------------------------------------------------ the rank-local mesh
+
+void build_host_mesh(int64_t nv, int64_t ne, const double* xy, const int32_t* cells, int rank,
+                     int nranks, int reorder, HostMesh& m) {
+  if (nv <= 0 || ne <= 0) throw std::runtime_error("empty mesh");
+  if (nv > 2000000000LL || ne > 2000000000LL / 3) throw std::runtime_error("mesh too large for int32 indices");
+  for (int64_t i = 0; i < 3 * ne; ++i)
+    if (cells[i] < 0 || cells[i] >= nv) throw std::runtime_error("cell vertex id out of range");
+  m.nv_g = nv; m.ne_g = ne; m.rank = rank; m.nranks = nranks;
+  std::vector<int32_t> order;
+  if (reorder) order = morton_order(nv, xy);
+  else { order.resize(nv); std::iota(order.begin(), order.end(), 0); }
+  std::vector<int32_t> posof(nv);
+  for (int64_t p = 0; p < nv; ++p) posof[order[p]] = (int32_t)p;
+  std::vector<int64_t> bounds(nranks + 1);
+  for (int r = 0; r <= nranks; ++r) bounds[r] = (nv * (int64_t)r) / nranks;
+  auto owner_of_pos = [&](int64_t p) {
+    return (int)(std::upper_bound(bounds.begin(), bounds.end(), p) - bounds.begin()) - 1;
+  };
+  const int64_t lo = bounds[rank], hi = bounds[rank + 1];
+  m.n_owned = (int32_t)(hi - lo);
+  // local cells (any owned vertex) and ghost vertices
+  std::vector<int32_t> lc;
+  std::vector<int32_t> ghost_pos;
+  if (nranks == 1) {
+    lc.resize(ne);
+    std::iota(lc.begin(), lc.end(), 0);
+  } else {
+    std::vector<uint8_t> seen(nv, 0);
+    for (int64_t e = 0; e < ne; ++e) {
+      bool any = false;
+      for (int i = 0; i < 3; ++i) {
+        int64_t p = posof[cells[3 * e + i]];
+        any |= (p >= lo && p < hi);
+      }
+      if (!any) continue;
+      lc.push_back((int32_t)e);
+      for (int i = 0; i < 3; ++i) {
+        int32_t v = cells[3 * e + i];
+        int64_t p = posof[v];
+        if ((p < lo || p >= hi) && !seen[v]) { seen[v] = 1; ghost_pos.push_back((int32_t)p); }
+      }
+    }
+    std::sort(ghost_pos.begin(), ghost_pos.end());
+  }
+  m.n_local = m.n_owned + (int32_t)ghost_pos.size();
+  m.l2g.resize(m.n_local);
+  for (int64_t p = lo; p < hi; ++p) m.l2g[p - lo] = order[p];
+  for (size_t k = 0; k < ghost_pos.size(); ++k) m.l2g[m.n_owned + k] = order[ghost_pos[k]];
+  m.g2l.assign(nv, -1);
+  for (int32_t l = 0; l < m.n_local; ++l) m.g2l[m.l2g[l]] = l;
+  // cells in local ids, sorted by min local vertex id (stable => ties by caller cell id)
+  m.ne = (int32_t)lc.size();
+  {
+    std::vector<std::pair<int32_t, int32_t>> key(m.ne);
+    for (int32_t k = 0; k < m.ne; ++k) {
+      const int32_t* c = cells + 3 * (int64_t)lc[k];
+      key[k] = {std::min(m.g2l[c[0]], std::min(m.g2l[c[1]], m.g2l[c[2]])), lc[k]};
+    }
+    if (reorder) std::stable_sort(key.begin(), key.end(), [](auto& a, auto& b) { return a.first < b.first; });
+    m.cell_l2g.resize(m.ne);
+    m.cells.resize(3 * (size_t)m.ne);
+    for (int32_t k = 0; k < m.ne; ++k) {
+      m.cell_l2g[k] = key[k].second;
+      const int32_t* c = cells + 3 * (int64_t)key[k].second;
+      for (int i = 0; i < 3; ++i) m.cells[3 * (size_t)k + i] = m.g2l[c[i]];
+    }
+  }
+  m.x.resize(m.n_local);
+  m.y.resize(m.n_local);
+  for (int32_t l = 0; l < m.n_local; ++l) { m.x[l] = xy[2 * (int64_t)m.l2g[l]]; m.y[l] = xy[2 * (int64_t)m.l2g[l] + 1]; }
+  // CSR of owned rows
+  const int32_t no = m.n_owned;
+  m.A = adjacency(no, m.n_local, m.ne, m.cells.data(), [no](int32_t v) { return v < no ? (int64_t)v : (int64_t)-1; });
+  {
+    std::vector<int32_t> diag(no);
+    std::iota(diag.begin(), diag.end(), 0);
+    finish_rows(m.A, diag);
+  }
+  m.S = sell_from_csr(m.A);
+  // slot table and diagonal positions
+  m.slot.assign(9 * (size_t)m.ne, -1);
+  auto find = [&](int32_t r, int32_t c) -> int32_t {
+    const int32_t* b = m.A.col.data() + m.A.rowptr[r];
+    const int32_t* e = m.A.col.data() + m.A.rowptr[r + 1];
+    const int32_t* p = std::lower_bound(b, e, c);
+    return (int32_t)m.S.pos(r, (int)(p - b));
+  };
+  for (int32_t e = 0; e < m.ne; ++e)
+    for (int a = 0; a < 3; ++a) {
+      int32_t r = m.cells[3 * (size_t)e + a];
+      if (r >= no) continue;
+      for (int b = 0; b < 3; ++b) m.slot[(size_t)(3 * a + b) * m.ne + e] = find(r, m.cells[3 * (size_t)e + b]);
+    }
+  m.diag_pos.resize(no);
+  for (int32_t r = 0; r < no; ++r) m.diag_pos[r] = find(r, r);
+  // winning cell: highest caller cell id containing the vertex
+  m.win_cell.assign(no, -1);
+  std::vector<int32_t> win_local(no, -1);
+  for (int32_t e = 0; e < m.ne; ++e)
+    for (int a = 0; a < 3; ++a) {
+      int32_t r = m.cells[3 * (size_t)e + a];
+      if (r < no && m.cell_l2g[e] > m.win_cell[r]) { m.win_cell[r] = m.cell_l2g[e]; win_local[r] = e; }
+    }
+  m.win.assign(4 * (size_t)no, 0);
+  for (int32_t r = 0; r < no; ++r) {
+    int32_t e = win_local[r];
+    if (e < 0) {  // isolated vertex: degenerate 'cell' of itself (gradients vanish)
+      m.win[4 * (size_t)r] = m.win[4 * (size_t)r + 1] = m.win[4 * (size_t)r + 2] = r;
+      m.win[4 * (size_t)r + 3] = -1;
+      continue;
+    }
+    int loc = 0;
+    for (int a = 0; a < 3; ++a) {
+      m.win[4 * (size_t)r + a] = m.cells[3 * (size_t)e + a];
+      if (m.cells[3 * (size_t)e + a] == r) loc = a;
+    }
+    m.win[4 * (size_t)r + 3] = loc;
+  }
+  // halo maps
+  m.nbrs.clear();
+  if (nranks > 1) {
+    std::vector<std::vector<int32_t>> send(nranks);
+    for (int32_t e = 0; e < m.ne; ++e) {
+      int own[3];
+      for (int a = 0; a < 3; ++a) own[a] = owner_of_pos(posof[m.l2g[m.cells[3 * (size_t)e + a]]]);
+      for (int a = 0; a < 3; ++a) {
+        if (own[a] != rank) continue;
+        for (int b = 0; b < 3; ++b)
+          if (own[b] != rank) send[own[b]].push_back(m.cells[3 * (size_t)e + a]);
+      }
+    }
+    std::vector<int32_t> rb(nranks, 0), rc(nranks, 0);
+    for (int32_t g = no; g < m.n_local; ++g) {
+      int o = owner_of_pos(posof[m.l2g[g]]);
+      if (rc[o] == 0) rb[o] = g;
+      rc[o]++;
+    }
+    for (int r = 0; r < nranks; ++r) {
+      auto& s = send[r];
+      std::sort(s.begin(), s.end());
+      s.erase(std::unique(s.begin(), s.end()), s.end());
+      if (s.empty() && rc[r] == 0) continue;
+      Neighbor nb;
+      nb.rank = r;
+      nb.send_local = s;
+      nb.recv_begin = rb[r];
+      nb.recv_count = rc[r];
+      m.nbrs.push_back(std::move(nb));
+    }
+  }
+}
+
+}  // namespace shakti

@@ -1,0 +1,179 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs.  Tolerances are BASELINE.json's: CSR pattern bit-exact, residual/Jacobian 1e-12
+relative (infinity norm), fields 1e-8 relative after the same number of steps."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from common import make_case, make_model, make_oracle, relinf
+
+pytestmark = pytest.mark.gpu
+
+DT = 3600.0
+
+
+@pytest.fixture(scope="module", params=[dict(reorder=1), dict(reorder=0)], ids=["morton", "caller-order"])
+def case(request):
+    c = make_case()
+    o = make_oracle(*c)
+    m = make_model(*c, **request.param)
+    yield c, o, m
+    m.close()
+
+
+def test_csr_pattern_bit_exact(case):
+    _, o, m = case
+    rowptr, col = m.csr()
+    assert rowptr.dtype == np.int32 and col.dtype == np.int32
+    assert np.array_equal(rowptr, o.rowptr) and np.array_equal(col, o.col)
+
+
+def test_winning_cells(case):
+    _, o, m = case
+    assert np.array_equal(m.winning_cells(), o.win_cell)
+
+
+def test_kbar(case):
+    _, o, m = case
+    assert relinf(m.kbar(), o.kbar()) < 1e-13
+
+
+def test_residual_and_jacobian(case):
+    _, o, m = case
+    F, J = m.assemble(DT)
+    Fo, Jo = o.assemble(DT)
+    assert relinf(F, Fo) < 1e-12
+    assert relinf(J, Jo) < 1e-12
+
+
+def test_spmv(case):
+    _, o, m = case
+    m.assemble(DT)
+    _, Jo = o.assemble(DT)
+    x = np.random.default_rng(3).standard_normal(o.nv)
+    y = m.spmv(x)
+    assert relinf(y, o.jacobian_matrix(Jo) @ x) < 1e-13
+
+
+@pytest.mark.parametrize("ksp,pc", [("gmres", "jacobi"), ("gmres", "amg"), ("bicgstab", "jacobi"), ("bicgstab", "amg")])
+def test_linear_solve(case, ksp, pc):
+    _, o, m = case
+    m.set_options(linear_solver=ksp, precond=pc, linear_rtol=1e-12, linear_max_it=5000)
+    m.assemble(DT)
+    Fo, Jo = o.assemble(DT)
+    A = o.jacobian_matrix(Jo).tocsc()
+    ref = spla.splu(A).solve(Fo)
+    dx, its, relres = m.linear_solve(Fo)
+    assert relres <= 1e-11
+    assert relinf(dx, ref) < 1e-7, (its, relres)
+
+
+def test_nodal_updates(case):
+    c, o, m = case
+    # state after a fake "solve": N = N_n perturbed
+    rng = np.random.default_rng(5)
+    N = c[2]["N_n"] * (1 + 0.01 * rng.standard_normal(o.nv))
+    o.N = N.copy()
+    m.set_field("N", N)
+    o.update_q(); m.update_q()
+    assert relinf(m.get_flux(), o.q) < 1e-13
+    o.update_melt(); m.update_melt()
+    assert relinf(m.get_field("melt_n"), o.melt_n) < 1e-13
+    o.update_b(DT); m.update_b(DT)
+    assert relinf(m.get_field("b"), o.b) < 1e-13
+
+
+@pytest.mark.parametrize("r0", ["dolfinx", "initial_residual"])
+@pytest.mark.parametrize("pc", ["jacobi", "amg"])
+def test_transient_fields(pc, r0):
+    c = make_case(seed=2)
+    o = make_oracle(*c, newton_r0=r0)
+    m = make_model(*c, precond=pc, newton_r0=r0, linear_max_it=5000)
+    try:
+        ts = np.linspace(0, 8 * DT, 9)
+        dts = o.dt_schedule(ts)[:6]
+        its_o = [o.step(dt)[0] for dt in dts]
+        its_m = list(m.run(dts))
+        assert its_m == its_o
+        assert relinf(m.get_field("N"), o.N) < 1e-8
+        assert relinf(m.get_field("b"), o.b) < 1e-8
+        assert relinf(m.get_flux(), o.q) < 1e-8
+        assert relinf(m.get_field("melt_n"), o.melt_n) < 1e-8
+        assert relinf(m.get_field("N_n"), o.N_n) < 1e-8
+    finally:
+        m.close()
+
+
+def test_negative_gap_height_first_step():
+    """setup_cooke2.py:66: b_init is negative at ~40% of nodes and only clamped after step 0.
+    K ~ |b|^3 then jumps by ~1e9 between neighbouring cells and the Jacobian is so badly
+    conditioned that LU itself carries O(cond * eps) > 1e-8 error in N; so the solve is checked
+    through the nonlinear residual (evaluated by the oracle at the GPU's N), N to 1e-6, and the
+    nodal updates + clamp to 1e-12 from identical N."""
+    c = make_case(seed=4, neg_b=True, turbulent=False)
+    o = make_oracle(*c)
+    m = make_model(*c, precond="amg", linear_max_it=5000, linear_rtol=1e-14)
+    try:
+        F, J = m.assemble(DT)
+        Fo, Jo = o.assemble(DT)
+        assert relinf(F, Fo) < 1e-12 and relinf(J, Jo) < 1e-12
+        o.newton(360.0)
+        m.newton_solve(360.0)
+        Ng = m.get_field("N")
+        Fg, _ = o.assemble(360.0, N=Ng, want_J=False)
+        assert np.linalg.norm(Fg) <= max(10 * o.residual_history[-1], 1e-9 * o.residual_history[0])
+        assert relinf(Ng, o.N) < 1e-6
+        m.set_field("N", o.N)
+        for upd_o, upd_m in ((o.update_q, m.update_q), (o.update_melt, m.update_melt),
+                             (lambda: o.update_b(360.0), lambda: m.update_b(360.0))):
+            upd_o(); upd_m()
+        bg = m.get_field("b")
+        assert bg.min() >= 1e-5 and (bg == 1e-5).sum() == (o.b == 1e-5).sum() > 0
+        assert relinf(bg, o.b) < 1e-12
+        assert relinf(m.get_flux(), o.q) < 1e-12
+    finally:
+        m.close()
+
+
+def test_no_dirichlet_and_no_storage():
+    c = list(make_case(seed=6, storage=False))
+    c[3] = np.zeros(0, dtype=np.int32)
+    o = make_oracle(*c)
+    m = make_model(*c, precond="amg")
+    try:
+        F, J = m.assemble(DT)
+        Fo, Jo = o.assemble(DT)
+        assert relinf(F, Fo) < 1e-12 and relinf(J, Jo) < 1e-12
+        o.step(DT); m.step(DT)
+        assert relinf(m.get_field("N"), o.N) < 1e-8
+    finally:
+        m.close()
+
+
+def test_custom_quadrature_table():
+    from oracle import quadrature
+    c = make_case(seed=7)
+    pts, wts = quadrature.gauss_jacobi_triangle(10)
+    o = make_oracle(*c, quad=(pts, wts))
+    m = make_model(*c)
+    try:
+        m.set_quadrature(pts, wts)
+        assert relinf(m.kbar(), o.kbar()) < 1e-13
+        F, J = m.assemble(DT)
+        Fo, Jo = o.assemble(DT)
+        assert relinf(F, Fo) < 1e-12 and relinf(J, Jo) < 1e-12
+    finally:
+        m.close()
+
+
+def test_newton_failure_is_reported():
+    from shakti_b200 import capi
+    c = make_case(seed=8)
+    m = make_model(*c, newton_max_it=0, newton_r0="initial_residual", newton_rtol=0.0, newton_atol=0.0)
+    try:
+        with pytest.raises(capi.ShaktiError) as e:
+            m.step(DT)
+        assert e.value.code == capi.ERR_NOT_CONVERGED
+    finally:
+        m.close()
