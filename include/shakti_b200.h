@@ -63,9 +63,14 @@ typedef enum shakti_field {
 
 typedef enum shakti_linear_solver { SHAKTI_KSP_GMRES = 0, SHAKTI_KSP_BICGSTAB = 1 } shakti_linear_solver;
 typedef enum shakti_precond { SHAKTI_PC_JACOBI = 0, SHAKTI_PC_AMG = 1, SHAKTI_PC_NONE = 2 } shakti_precond;
+/* Denominator of NewtonSolver's relative test ||F||/r0 < rtol (solvers.py:52,179 [EXT]).
+ * INITIAL_RESIDUAL (default): r0 = ||F||_2 at iteration 0 of the current solve (SURVEY.md row
+ * a11).  DOLFINX: r0 = ||dx||_2 of iteration 1, never reset between solves and 0 before the very
+ * first one -- what the DOLFINx 0.8/0.9 C++ class is believed to do; unverifiable offline, and
+ * scale dependent (a time step is skipped whenever ||F|| < rtol * ||dx_1|| of the previous step). */
 typedef enum shakti_newton_r0 {
-  SHAKTI_R0_DOLFINX = 0,          /* residual0 = ||dx||_2 of iteration 1, kept across solves (DOLFINx C++ NewtonSolver) */
-  SHAKTI_R0_INITIAL_RESIDUAL = 1  /* residual0 = ||F||_2 at iteration 0 */
+  SHAKTI_R0_DOLFINX = 0,
+  SHAKTI_R0_INITIAL_RESIDUAL = 1
 } shakti_newton_r0;
 
 /* Solver options.  Newton defaults are DOLFINx NewtonSolver's (solvers.py:52): rtol 1e-9,
@@ -77,7 +82,7 @@ typedef struct shakti_options {
   int32_t newton_r0;            /* shakti_newton_r0 */
   int32_t linear_solver;        /* shakti_linear_solver */
   int32_t precond;              /* shakti_precond */
-  double linear_rtol;           /* ||J dx - F|| <= linear_rtol * ||F||   */
+  double linear_rtol;           /* ||J dx - F_k|| <= linear_rtol * ||F_0|| (F_0: residual the Newton solve started from) */
   double linear_atol;
   int32_t linear_max_it;
   int32_t gmres_restart;
@@ -184,6 +189,9 @@ int shakti_copy_N_to_N_n(shakti_model* m);
 int shakti_step(shakti_model* m, double dt, int32_t* niter, int32_t* converged);
 /* nsteps passes with the given dt list; niter_out (nsteps int32) may be NULL. */
 int shakti_run(shakti_model* m, const double* dts, int64_t nsteps, int32_t* niter_out);
+/* shakti_run bracketed by CUDA events on the library's stream; *ms = device time of the nsteps
+ * steps (the caller barriers/synchronises around it and takes the max over ranks). */
+int shakti_run_timed(shakti_model* m, const double* dts, int64_t nsteps, int32_t* niter_out, double* ms);
 /* Same as shakti_step with host buffers in the call: copies `inputs_host` (n_vert doubles,
  * may be NULL) to the device before the step and b, N, qx, qy (each n_vert doubles, any may
  * be NULL) back after it — the per-save traffic of solvers.py:199-208. */

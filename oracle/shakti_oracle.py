@@ -84,7 +84,7 @@ def dirichlet_dofs(xy, cells, marker):
 
 
 class ShaktiOracle:
-    def __init__(self, xy, cells, params=None, quad=None, newton_r0="dolfinx"):
+    def __init__(self, xy, cells, params=None, quad=None, newton_r0="initial_residual"):
         self.xy = np.ascontiguousarray(xy, dtype=np.float64)
         self.cells = np.ascontiguousarray(cells, dtype=np.int32)
         self.nv = self.xy.shape[0]

@@ -359,6 +359,14 @@ class Model:
         _check(self.lib.shakti_run(self._h, _p(dts), C.c_int64(dts.size), _p(its)))
         return its
 
+    def run_timed(self, dts):
+        """run() bracketed by CUDA events on the library stream -> (niter per step, milliseconds)."""
+        dts = _f64(dts)
+        its = np.zeros(dts.size, dtype=np.int32)
+        ms = C.c_double(0)
+        _check(self.lib.shakti_run_timed(self._h, _p(dts), C.c_int64(dts.size), _p(its), C.byref(ms)))
+        return its, ms.value
+
     def step_host(self, dt, inputs_ptr=None, b_ptr=None, N_ptr=None, qx_ptr=None, qy_ptr=None):
         """shakti_step_host with raw host pointers (e.g. pinned torch tensors' data_ptr())."""
         it, cv = C.c_int32(0), C.c_int32(0)

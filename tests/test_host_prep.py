@@ -1,0 +1,148 @@
+"""Host-side preprocessing of the C-ABI library (no GPU needed): CSR pattern bit-exact against
+the oracle, Dirichlet location, internal ordering, SELL layout, scatter table, winning cells,
+partition + halo maps."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle.shakti_oracle import ShaktiOracle, csr_pattern, dirichlet_dofs
+from shakti_b200 import capi, meshgen
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "shakti_b200.h").read_text()
+    names = set(re.findall(r"\b(shakti_[a-z0-9_]+)\s*\(", header))
+    assert len(names) >= 40
+    lib = capi.load()
+    missing = [n for n in sorted(names) if not hasattr(lib, n)]
+    assert not missing, missing
+    assert lib.shakti_version().decode().startswith("shakti_b200")
+
+
+def test_struct_layouts_match_header():
+    o = capi.default_options()
+    assert (o.newton_rtol, o.newton_atol, o.newton_max_it) == (1e-9, 1e-10, 50)
+    assert o.b_min == 1e-5 and o.reorder == 1 and o.gmres_restart > 0
+    p = capi.default_params()
+    import sys
+    sys.path.insert(0, str(ROOT / "shakti-fenics_b200" / "source"))
+    import params
+    for k in params.NAMES:
+        assert getattr(p, k) == float(getattr(params, k))
+
+
+def test_create_without_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    xy, cells = meshgen.rectangle(2, 2, 1.0, 1.0)
+    with pytest.raises(capi.ShaktiError) as e:
+        capi.Model(xy, cells)
+    assert e.value.code in (-2, -3)
+
+
+@pytest.fixture(scope="module")
+def mesh():
+    xy, cells = meshgen.rectangle(40, 30, 100e3, 50e3, jitter=0.25, diagonal="random")
+    return meshgen.scramble(xy, cells)
+
+
+def test_csr_pattern_bit_exact(mesh):
+    xy, cells = mesh
+    rp, col = capi.host_csr_pattern(xy.shape[0], cells)
+    rp2, col2 = csr_pattern(xy.shape[0], cells)
+    assert rp.dtype == np.int32 and col.dtype == np.int32
+    assert np.array_equal(rp, rp2) and np.array_equal(col, col2)
+
+
+def test_locate_dirichlet(mesh):
+    xy, cells = mesh
+    d = capi.host_locate_dirichlet(xy.shape[0], cells, np.isclose(xy[:, 0], 0.0))
+    assert np.array_equal(d, dirichlet_dofs(xy, cells, lambda X: np.isclose(X[0], 0.0)))
+    assert capi.host_locate_dirichlet(xy.shape[0], cells, np.zeros(xy.shape[0], bool)).size == 0
+
+
+def _sell_to_csr(hm, vals, nv):
+    l2g = hm.array("l2g")
+    rowptr, lcol = hm.array("rowptr"), hm.array("col")
+    sp_, scol = hm.array("slice_ptr"), hm.array("sell_col")
+    rows, cols, vv = [], [], []
+    for r in range(hm.n_owned):
+        base = sp_[r >> 5] + (r & 31)
+        for k in range(rowptr[r + 1] - rowptr[r]):
+            p = base + 32 * k
+            assert scol[p] == lcol[rowptr[r] + k]
+            rows.append(l2g[r]); cols.append(l2g[scol[p]]); vv.append(vals[p])
+    return sp.csr_matrix((vv, (rows, cols)), shape=(nv, nv))
+
+
+@pytest.mark.parametrize("nranks", [1, 2, 3])
+@pytest.mark.parametrize("reorder", [0, 1])
+def test_rank_local_mesh(mesh, nranks, reorder):
+    xy, cells = mesh
+    nv = xy.shape[0]
+    o = ShaktiOracle(xy, cells)
+    rng = np.random.default_rng(0)
+    Ke = rng.standard_normal((cells.shape[0], 9))
+    ref = np.zeros(o.col.size)
+    np.add.at(ref, o.slot.ravel(), Ke.ravel())
+    Jref = sp.csr_matrix((ref, o.col, o.rowptr), shape=(nv, nv))
+    owned_all, hms = [], []
+    for r in range(nranks):
+        hm = capi.HostMesh(xy, cells, r, nranks, reorder)
+        hms.append(hm)
+        l2g = hm.array("l2g")
+        own = l2g[: hm.n_owned]
+        owned_all.append(own)
+        if reorder == 0 and nranks == 1:
+            assert np.array_equal(l2g, np.arange(nv))
+        lc, cl2g = hm.array("cells").reshape(-1, 3), hm.array("cell_l2g")
+        assert np.array_equal(l2g[lc], cells[cl2g])                       # vertex order inside cells kept
+        touched = np.isin(cells, own).any(axis=1)
+        assert np.array_equal(np.sort(cl2g), np.nonzero(touched)[0])      # exactly the cells touching owned rows
+        assert np.array_equal(hm.array("win_cell"), o.win_cell[own])      # winner by GLOBAL cell index
+        win = hm.array("win").reshape(-1, 4)
+        assert np.array_equal(l2g[win[np.arange(hm.n_owned), win[:, 3]]], own)
+        # scatter through the slot table reproduces the oracle's CSR values on owned rows
+        slot = hm.array("slot").reshape(9, -1)
+        vals = np.zeros(hm.padded)
+        m = slot >= 0
+        np.add.at(vals, slot[m], Ke[cl2g].T[m])
+        Jm = _sell_to_csr(hm, vals, nv)
+        assert abs(Jm[own] - Jref[own]).max() < 1e-12
+        scol, dp = hm.array("sell_col"), hm.array("diag_pos")
+        assert np.array_equal(scol[dp], np.arange(hm.n_owned))
+    allo = np.concatenate(owned_all)
+    assert np.array_equal(np.sort(allo), np.arange(nv))                   # a partition of the dofs
+    # halo maps are consistent pairwise: what r sends to s is what s expects from r, in order
+    for r, hm in enumerate(hms):
+        ranks, sptr, sidx = hm.array("nbr_rank"), hm.array("nbr_send_ptr"), hm.array("nbr_send_idx")
+        l2g = hm.array("l2g")
+        for k, s in enumerate(ranks):
+            sent = l2g[sidx[sptr[k]: sptr[k + 1]]]
+            h2 = hms[s]
+            r2, recv, l2g2 = h2.array("nbr_rank"), h2.array("nbr_recv").reshape(-1, 2), h2.array("l2g")
+            kk = int(np.nonzero(r2 == r)[0][0])
+            assert np.array_equal(sent, l2g2[recv[kk, 0]: recv[kk, 0] + recv[kk, 1]])
+
+
+def test_morton_order_is_local():
+    """Rows of a 32-row slice should sit close together in space (SpMV gather locality)."""
+    xy, cells = meshgen.rectangle(64, 64, 64.0, 64.0)
+    hm = capi.HostMesh(xy, cells)
+    l2g = hm.array("l2g")
+    p = xy[l2g]
+    spans = [np.ptp(p[s: s + 32], axis=0).max() for s in range(0, 32 * (len(p) // 32), 32)]
+    assert np.median(spans) <= 8.0
+
+
+def test_invalid_mesh_is_rejected():
+    xy = np.zeros((3, 2))
+    with pytest.raises(capi.ShaktiError):
+        capi.HostMesh(xy, np.array([[0, 1, 5]], dtype=np.int32))

@@ -1,0 +1,170 @@
+"""The CPU oracle against independent mathematics (the reference ships no tests or golden
+vectors and cannot run here: SURVEY.md §8c, "parity unpinned")."""
+import json
+from math import factorial
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from common import make_case, make_oracle, relinf
+from oracle import quadrature
+from oracle.shakti_oracle import Params, ShaktiOracle, csr_pattern, dirichlet_dofs
+
+GOLDEN = json.loads((Path(__file__).parent / "golden" / "element_golden.json").read_text())
+
+
+@pytest.mark.parametrize("rule,deg", [(quadrature.gauss_jacobi_triangle(7), 7), (quadrature.radon7(), 5),
+                                      (quadrature.gauss_jacobi_triangle(10), 10)])
+def test_quadrature_exact_for_monomials(rule, deg):
+    p, w = rule
+    assert abs(w.sum() - 0.5) < 1e-15
+    for a in range(deg + 1):
+        for b in range(deg + 1 - a):
+            exact = factorial(a) * factorial(b) / factorial(a + b + 2)
+            assert abs((w * p[:, 0] ** a * p[:, 1] ** b).sum() - exact) < 2e-16 + 1e-14 * exact
+
+
+def _single_element_oracle(case):
+    xy = np.array(case["xy"])
+    o = ShaktiOracle(xy, np.array([[0, 1, 2]], dtype=np.int32))
+    f = case["fields"]
+    for k in ("z_b", "z_s", "G", "inputs", "storage", "b", "N_n", "melt_n"):
+        getattr(o, k)[:] = f[k]
+    o.N = np.array(f["N"])
+    o.q[:, 0], o.q[:, 1] = f["qx"], f["qy"]
+    return o
+
+
+@pytest.mark.parametrize("idx", range(len(GOLDEN["cases"])))
+def test_element_integrals_match_exact_sympy_fixture(idx):
+    """tests/golden/element_golden.json holds EXACT (sympy rational) integrals of the weak form
+    solvers.py:45 and its derivative on single triangles, see make_element_golden.py."""
+    case = GOLDEN["cases"][idx]
+    o = _single_element_oracle(case)
+    Fe, Je = o.element_FJ(case["dt"])
+    Fe, Je = Fe[0], Je[0]
+    if case["kind"] == "poly":          # fixture excludes the (non-polynomial) K term: remove it
+        kb = o.kbar()[0]
+        gh = o._cell_grad(o.head(o.N))[0]
+        gp = o.gradphi[0]
+        Fe = Fe - kb * gp @ gh
+        Je = Je + kb / (o.p.rho_w * o.p.g) * gp @ gp.T
+    Fg, Jg = np.array(case["F"]), np.array(case["J"])
+    assert np.max(np.abs(Fe - Fg)) <= 1e-12 * np.max(np.abs(Fg))
+    assert np.max(np.abs(Je - Jg)) <= 1e-12 * np.max(np.abs(Jg))
+
+
+def test_jacobian_matches_finite_differences():
+    c = make_case(nx=10, ny=8, seed=3)
+    o = make_oracle(*c)
+    F, vals = o.assemble(3600.0)
+    J = o.jacobian_matrix(vals)
+    rng = np.random.default_rng(0)
+    v = rng.standard_normal(o.nv)
+    v[o.bc_dofs] = 0
+    eps = 0.1
+    Fp, _ = o.assemble(3600.0, o.N + eps * v, want_J=False)
+    Fm, _ = o.assemble(3600.0, o.N - eps * v, want_J=False)
+    fd, an = (Fp - Fm) / (2 * eps), J @ v
+    interior = np.ones(o.nv, bool)
+    interior[o.bc_dofs] = False
+    assert np.max(np.abs(fd - an)[interior]) < 1e-7 * np.max(np.abs(an)[interior])
+
+
+def test_patch_linear_head_gives_zero_flux_divergence():
+    """With b constant, q = 0 and every reaction term off, a linear head field has zero interior residual."""
+    from shakti_b200 import meshgen
+    xy, cells = meshgen.rectangle(8, 6, 8e3, 6e3, jitter=0.2, diagonal="random")
+    p = Params(A=0.0)
+    o = ShaktiOracle(xy, cells, params=p)
+    o.b[:] = 2e-3
+    o.z_b[:] = 0.0
+    o.z_s[:] = 0.0
+    o.N = -(p.rho_w * p.g) * (0.01 * xy[:, 0] + 0.02 * xy[:, 1])     # h = -N/(rho_w g) linear
+    o.N_n = o.N.copy()
+    F, _ = o.assemble(3600.0, want_J=False)
+    from oracle.shakti_oracle import boundary_facets
+    bnd = np.unique(boundary_facets(cells))
+    interior = np.setdiff1d(np.arange(o.nv), bnd)
+    assert np.max(np.abs(F[interior])) < 1e-12 * np.max(np.abs(F[bnd]))
+
+
+def test_stiffness_rows_sum_to_zero():
+    c = make_case(nx=8, ny=6, seed=1, storage=False)
+    o = make_oracle(*c)
+    o.p.A = 0.0
+    o.set_dirichlet([], 0.0)
+    o.q[:] = 0.0        # removes the advection part
+    _, vals = o.assemble(3600.0)
+    J = o.jacobian_matrix(vals)
+    assert np.max(np.abs(J @ np.ones(o.nv))) < 1e-12 * np.max(np.abs(vals))
+
+
+def test_dirichlet_handling():
+    c = make_case(nx=8, ny=6, seed=2)
+    o = make_oracle(*c)
+    o.N[o.bc_dofs] = o.N_bdry + 7.0   # violate the BC: lifting must act
+    F, vals = o.assemble(3600.0)
+    J = o.jacobian_matrix(vals).toarray()
+    bc = o.bc_dofs
+    assert np.allclose(F[bc], 7.0)
+    assert np.allclose(J[bc][:, bc], np.eye(bc.size))
+    off = np.ones(o.nv, bool)
+    off[bc] = False
+    assert np.all(J[bc][:, off] == 0) and np.all(J[off][:, bc] == 0)
+    # one Newton update restores the boundary value exactly
+    dx = np.linalg.solve(J, F)
+    assert np.allclose((o.N - dx)[bc], o.N_bdry)
+
+
+def test_last_cell_wins_interpolation():
+    c = make_case(nx=6, ny=5, seed=5)
+    o = make_oracle(*c)
+    vals = np.arange(o.ne * 3, dtype=float).reshape(o.ne, 3)
+    out = o._expr_at_vertices(vals)
+    ref = np.zeros(o.nv)
+    for cidx in range(o.ne):            # the literal DOLFINx loop
+        for i in range(3):
+            ref[o.cells[cidx, i]] = vals[cidx, i]
+    assert np.array_equal(out, ref)
+
+
+def test_dt_schedule_and_step_order():
+    t = np.array([0.0, 10.0, 25.0, 27.0])
+    assert np.allclose(ShaktiOracle.dt_schedule(t), [1.0, 10.0, 15.0, 2.0])
+    c = make_case(nx=8, ny=6, seed=6)
+    o = make_oracle(*c)
+    its = o.run(np.linspace(0, 3 * 3600.0, 4), nsteps=3)
+    assert len(its) == 3 and np.array_equal(o.N, o.N_n)
+    assert o.b.min() >= o.b_min
+
+
+@pytest.mark.parametrize("mode", ["initial_residual", "dolfinx"])
+def test_newton_modes_converge_to_same_root(mode):
+    c = make_case(nx=8, ny=6, seed=7)
+    o = make_oracle(*c, newton_r0=mode)
+    it, conv = o.newton(3600.0)
+    assert conv and it >= 1
+    F, _ = o.assemble(3600.0, want_J=False)
+    denom = o.residual_history[0] if mode == "initial_residual" else o._residual0   # ||F_0|| or ||dx_1||
+    assert np.linalg.norm(F) < 1e-9 * denom
+
+
+def test_newton_raises_when_not_converged():
+    c = make_case(nx=8, ny=6, seed=8)
+    o = make_oracle(*c)
+    o.max_it = 0
+    o.rtol = o.atol = 0.0
+    with pytest.raises(RuntimeError):
+        o.newton(3600.0)
+
+
+def test_csr_pattern_and_dirichlet_dofs_small():
+    xy = np.array([[0, 0], [1, 0], [1, 1], [0, 1.0]])
+    cells = np.array([[0, 1, 2], [0, 2, 3]], dtype=np.int32)
+    rp, col = csr_pattern(4, cells)
+    assert rp.tolist() == [0, 4, 7, 11, 14]
+    assert col.tolist() == [0, 1, 2, 3, 0, 1, 2, 0, 1, 2, 3, 0, 2, 3]
+    d = dirichlet_dofs(xy, cells, lambda x: np.isclose(x[0], 0.0))
+    assert d.tolist() == [0, 3]
