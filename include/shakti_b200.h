@@ -86,12 +86,16 @@ typedef struct shakti_options {
   double linear_atol;
   int32_t linear_max_it;
   int32_t gmres_restart;
-  int32_t amg_refresh_every;    /* recompute AMG numerics every k-th Newton solve (>=1) */
+  int32_t amg_refresh_every;    /* recompute AMG numerics at the first Newton solve of every k-th time step (>=1) */
   int32_t amg_max_levels;
   int32_t amg_coarse_size;      /* stop coarsening below this many rows */
-  int32_t amg_presmooth, amg_postsmooth;
+  int32_t amg_presmooth, amg_postsmooth; /* Jacobi sweeps, or Chebyshev polynomial degree */
   double amg_smoother_omega;    /* damped-Jacobi weight on every level */
   double amg_prolong_omega;     /* prolongator smoothing weight (0 = plain aggregation) */
+  double amg_strength_theta;    /* strong connection: |a_ij| >= theta 0.5^level sqrt(|a_ii a_jj|) (0 = all) */
+  double amg_cheby_ratio;       /* Chebyshev smoothing interval [lmax/ratio, lmax] of D^-1 A */
+  int32_t amg_smoother;         /* 0 = damped Jacobi, 1 = Chebyshev */
+  int32_t amg_reserved;
   double b_min;                 /* md.b_min, model_setup.py:53 */
   int32_t assembly_kernel;      /* 0 = row-block staged gather (default), 1 = element atomics */
   int32_t reorder;              /* 1 = internal Morton reordering (default), 0 = keep caller order */

@@ -10,9 +10,11 @@ namespace shakti {
 
 // ------------------------------------------------------------------ host: aggregation + patterns
 
-// Greedy (Vanek) aggregation on the pattern graph of the square block of A.
+// Greedy (Vanek) aggregation on the graph of STRONG connections of the square block of A
+// (strong[k] != 0 for CSR entry k; empty = every connection is strong).
 // Returns agg[i] in [0,n_agg) or -1 for excluded rows.
-static int aggregate(const HostCsr& A, int32_t n, const std::vector<uint8_t>& excl, std::vector<int32_t>& agg) {
+static int aggregate(const HostCsr& A, int32_t n, const std::vector<uint8_t>& excl, const std::vector<uint8_t>& strong,
+                     std::vector<int32_t>& agg) {
   agg.assign(n, -1);
   std::vector<uint8_t> free_(n, 1);
   for (int32_t i = 0; i < n; ++i)
@@ -21,7 +23,7 @@ static int aggregate(const HostCsr& A, int32_t n, const std::vector<uint8_t>& ex
   auto nb = [&](int32_t i, auto&& f) {
     for (int32_t k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k) {
       const int32_t j = A.col[k];
-      if (j < n && j != i && (excl.empty() || !excl[j])) f(j);
+      if (j < n && j != i && (excl.empty() || !excl[j]) && (strong.empty() || strong[k])) f(j);
     }
   };
   // pass 1: roots whose whole neighbourhood is free
@@ -263,6 +265,82 @@ __global__ void amg_dense_apply_kernel(int32_t n, const double* __restrict__ D, 
   if (lane == 0) x[warp] = acc;
 }
 
+// ------------------------------------------------------------------ smoother kernels
+// deterministic pseudo-random start vector for the power iteration
+__global__ void amg_hash_fill_kernel(int32_t n, double* __restrict__ x) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t h = (uint32_t)i * 2654435761u;
+  h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13;
+  x[i] = 0.5 + (double)(h & 0xffffff) / 16777216.0;
+}
+// y = dinv .* (A x)
+__global__ void __launch_bounds__(256)
+amg_dinv_spmv_kernel(SellView A, const double* __restrict__ dinv, const double* __restrict__ x, double* __restrict__ y) {
+  const int32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= A.n_rows) return;
+  const int32_t base = A.slice_ptr[row >> 5] + (row & 31);
+  const int32_t w = (A.slice_ptr[(row >> 5) + 1] - A.slice_ptr[row >> 5]) >> 5;
+  double acc = 0.0;
+  for (int k = 0; k < w; ++k) acc += A.val[base + 32 * k] * x[A.col[base + 32 * k]];
+  y[row] = dinv[row] * acc;
+}
+// Chebyshev step: r = dinv (b - A x); d = c1 d + c2 r; x_out = x + d
+__global__ void __launch_bounds__(256)
+amg_cheby_kernel(SellView A, const double* __restrict__ dinv, const double* __restrict__ b, const double* __restrict__ x,
+                 double* __restrict__ d, double* __restrict__ x_out, double c1, double c2) {
+  const int32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+  const int32_t slice = row >> 5;
+  if (slice >= A.n_slices) return;
+  const int32_t base = A.slice_ptr[slice];
+  const int32_t w = (A.slice_ptr[slice + 1] - base) >> 5;
+  const int32_t* __restrict__ cp = A.col + base + (row & 31);
+  const double* __restrict__ vp = A.val + base + (row & 31);
+  double acc = 0.0;
+#pragma unroll 4
+  for (int k = 0; k < w; ++k) acc += vp[32 * k] * x[cp[32 * k]];
+  if (row >= A.n_rows) return;
+  const double r = dinv[row] * (b[row] - acc);
+  const double dn = c1 * d[row] + c2 * r;
+  d[row] = dn;
+  x_out[row] = x[row] + dn;
+}
+// first Chebyshev step from a zero guess: d = (dinv b)/theta ; x = d
+__global__ void amg_cheby_first_kernel(int32_t n, const double* __restrict__ dinv, const double* __restrict__ b,
+                                       double inv_theta, double* __restrict__ d, double* __restrict__ x) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double v = dinv[i] * b[i] * inv_theta;
+  d[i] = v;
+  x[i] = v;
+}
+
+// x = y / sqrt(nrm2[0])   (power-iteration normalisation without a host round trip)
+__global__ void amg_normalize_kernel(int32_t n, const double* __restrict__ y, const double* __restrict__ nrm2,
+                                     double* __restrict__ x) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double s = nrm2[0] > 0 ? rsqrt(nrm2[0]) : 0.0;
+  x[i] = y[i] * s;
+}
+// Gershgorin bound of lambda_max(D^-1 A): max_i |dinv_i| sum_j |a_ij|, reduced with an integer
+// atomicMax on the bit pattern (valid for non-negative doubles)
+__global__ void __launch_bounds__(256)
+amg_gershgorin_kernel(SellView A, const double* __restrict__ dinv, unsigned long long* __restrict__ out) {
+  const int32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+  double v = 0.0;
+  if (row < A.n_rows) {
+    const int32_t base = A.slice_ptr[row >> 5] + (row & 31);
+    const int32_t w = (A.slice_ptr[(row >> 5) + 1] - A.slice_ptr[row >> 5]) >> 5;
+    double acc = 0.0;
+    for (int k = 0; k < w; ++k) acc += fabs(A.val[base + 32 * k]);
+    v = fabs(dinv[row]) * acc;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0 && v > 0.0) atomicMax(out, (unsigned long long)__double_as_longlong(v));
+}
+
 // ------------------------------------------------------------------ hierarchy
 struct AmgLevel {
   int32_t n = 0, n_cols = 0, n_coarse = 0;
@@ -273,18 +351,30 @@ struct AmgLevel {
   DevSell P, R, AP;
   DevBuf<uint8_t> pmap;
   DevBuf<int32_t> tmap;
-  DevBuf<double> x, x2, b, r;
+  DevBuf<double> x, x2, b, r, d, pv;
+  bool pv_init = false;       // pv holds the current power-iteration vector (warm start)
+  double lmax = 2.0;          // estimate of lambda_max(D^-1 A)
   bool last = false;
+  HostCsr hA;                 // host pattern (levels >= 1), kept for rebuilds of deeper levels
+  HostSell hS;
 };
 
 struct Amg::Impl {
   AmgOptions opt;
   cudaStream_t s = 0;
+  const HostCsr* A0 = nullptr;
+  const HostSell* S0 = nullptr;
+  std::vector<uint8_t> exclude;
   std::vector<std::unique_ptr<AmgLevel>> lv;
   DevBuf<double> dense;
   DevBuf<int> info;
   bool dense_coarse = false;
+  bool built = false;
   double op_complexity = 0.0;
+  Reducer red;
+  DevBuf<double> scal;
+  double* host_scal = nullptr;
+  ~Impl() { if (host_scal) cudaFreeHost(host_scal); }
 };
 
 Amg::Amg() : p_(new Impl()) {}
@@ -306,69 +396,166 @@ static std::vector<int32_t> diag_positions(const HostCsr& A, const HostSell& S, 
 
 void Amg::setup(const HostCsr& A0, const HostSell& S0, const std::vector<uint8_t>& exclude, const AmgOptions& opt,
                 int sm_count, cudaStream_t s) {
-  (void)sm_count;
   Impl& I = *p_;
   I.opt = opt;
   I.s = s;
+  I.A0 = &A0;
+  I.S0 = &S0;
+  I.exclude = exclude;
   I.lv.clear();
+  I.built = false;
+  I.red.init(sm_count);
+  I.scal.alloc_zero(4, s);
+  if (!I.host_scal) SHAKTI_CUDA(cudaMallocHost(&I.host_scal, 4 * sizeof(double)));
   refreshes_ = 0;
-  HostCsr Acur;            // levels >= 1 own their pattern
-  HostSell Scur;
-  const HostCsr* A = &A0;
-  const HostSell* S = &S0;
-  std::vector<uint8_t> excl = exclude;
+}
+
+static void alloc_level_vectors(AmgLevel& L, int level, cudaStream_t s) {
+  L.dinv.alloc_zero(std::max(L.n, 1), s);
+  L.x.alloc_zero(std::max(L.n_cols, 1), s);
+  L.x2.alloc_zero(std::max(L.n_cols, 1), s);
+  L.r.alloc_zero(std::max(L.n, 1), s);
+  L.d.alloc_zero(std::max(L.n, 1), s);
+  L.pv.alloc_zero(std::max(L.n_cols, 1), s);
+  if (level > 0) L.b.alloc_zero(std::max(L.n, 1), s);
+}
+
+// numeric phase of one level: smoother diagonal, P, R, AP and the next level's operator
+static void numeric_level(Amg::Impl& I, size_t l, const DevSell& Afine, const int32_t* fine_diag_pos) {
+  cudaStream_t s = I.s;
+  AmgLevel& L = *I.lv[l];
+  const DevSell& A = (l == 0) ? Afine : L.A;
+  const int32_t* dpos = (l == 0) ? fine_diag_pos : L.diag_pos.p;
+  if (L.n > 0) SHAKTI_LAUNCH(amg_dinv_kernel, div_up(L.n, 256), 256, 0, s, L.n, dpos, A.val.p, L.dinv.p);
+  if (L.last || L.n == 0) return;
+  SHAKTI_CUDA(cudaMemsetAsync(L.P.val.p, 0, sizeof(double) * L.P.padded, s));
+  SHAKTI_LAUNCH(amg_prolongator_kernel, div_up(L.n, 256), 256, 0, s, view(A), L.pmap.p, dpos, L.dinv.p,
+                I.opt.prolong_omega, L.P.slice_ptr.p, L.P.val.p);
+  SHAKTI_LAUNCH(amg_gather_vals_kernel, (int)std::min<int64_t>(148 * 8, std::max<int64_t>(1, (L.R.padded + 255) / 256)), 256, 0, s,
+                L.R.padded, L.tmap.p, L.P.val.p, L.R.val.p);
+  SHAKTI_CUDA(cudaMemsetAsync(L.AP.val.p, 0, sizeof(double) * L.AP.padded, s));
+  SHAKTI_LAUNCH(amg_spgemm_kernel, div_up(L.n, 128), 128, 0, s, view(A), A.rowlen.p, view(L.P), L.P.rowlen.p, L.P.n_rows,
+                L.AP.slice_ptr.p, L.AP.col.p, L.AP.rowlen.p, L.AP.val.p);
+  DevSell& Ac = I.lv[l + 1]->A;
+  SHAKTI_CUDA(cudaMemsetAsync(Ac.val.p, 0, sizeof(double) * Ac.padded, s));
+  SHAKTI_LAUNCH(amg_spgemm_kernel, div_up(L.R.n_rows, 128), 128, 0, s, view(L.R), L.R.rowlen.p, view(L.AP), L.AP.rowlen.p,
+                L.AP.n_rows, Ac.slice_ptr.p, Ac.col.p, Ac.rowlen.p, Ac.val.p);
+}
+
+// Upper end of the spectrum of D^-1 A for the Chebyshev smoother, re-estimated at every refresh:
+// min(Gershgorin bound, 1.1 x power-iteration estimate).  The power vector is kept per level, so
+// a few iterations suffice once it is warm.  One host synchronisation per level.
+static double estimate_lmax(Amg::Impl& I, AmgLevel& L, const DevSell& A) {
+  cudaStream_t s = I.s;
+  if (L.n == 0) return 1.0;
+  const int grid = div_up(L.n, 256);
+  double* x = L.pv.p;   // n_cols long, entries beyond n stay 0
+  double* y = L.r.p;
+  int iters = 6;
+  if (!L.pv_init) {
+    SHAKTI_LAUNCH(amg_hash_fill_kernel, grid, 256, 0, s, L.n, x);
+    L.pv_init = true;
+    iters = 20;
+  }
+  for (int it = 0; it < iters; ++it) {
+    SHAKTI_LAUNCH(amg_dinv_spmv_kernel, grid, 256, 0, s, view(A), L.dinv.p, x, y);
+    launch_multi_dot(I.red, L.n, 1, y, L.n, y, I.scal.p, s);
+    SHAKTI_LAUNCH(amg_normalize_kernel, grid, 256, 0, s, L.n, y, I.scal.p, x);
+  }
+  SHAKTI_LAUNCH(amg_dinv_spmv_kernel, grid, 256, 0, s, view(A), L.dinv.p, x, y);
+  launch_multi_dot(I.red, L.n, 1, y, L.n, y, I.scal.p, s);       // ||D^-1 A x||^2 with ||x|| = 1
+  SHAKTI_CUDA(cudaMemsetAsync(I.scal.p + 1, 0, sizeof(double), s));
+  SHAKTI_LAUNCH(amg_gershgorin_kernel, grid, 256, 0, s, view(A), L.dinv.p, reinterpret_cast<unsigned long long*>(I.scal.p + 1));
+  SHAKTI_CUDA(cudaMemcpyAsync(I.host_scal, I.scal.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  SHAKTI_CUDA(cudaStreamSynchronize(s));
+  const double power = std::sqrt(std::max(I.host_scal[0], 0.0));
+  const double gersh = I.host_scal[1];
+  double lam = 1.1 * power;
+  if (gersh > 0 && (lam > gersh || !(power > 0) || !std::isfinite(power))) lam = gersh;
+  if (!(lam > 0) || !std::isfinite(lam)) lam = 2.0;
+  return lam;
+}
+
+static void update_smoother_bounds(Amg::Impl& I, const DevSell& Afine) {
+  for (size_t l = 0; l < I.lv.size(); ++l) {
+    AmgLevel& L = *I.lv[l];
+    const bool needed = I.opt.smoother == 1 && (!L.last || !I.dense_coarse);
+    L.lmax = needed ? estimate_lmax(I, L, l == 0 ? Afine : L.A) : 2.0;
+  }
+}
+
+static void build_hierarchy(Amg::Impl& I, const DevSell& Afine, const int32_t* fine_diag_pos) {
+  cudaStream_t s = I.s;
+  const AmgOptions& opt = I.opt;
+  I.lv.clear();
+  {
+    std::unique_ptr<AmgLevel> L0(new AmgLevel());
+    L0->n = (int32_t)I.A0->n_rows;
+    L0->n_cols = (int32_t)I.A0->n_cols;
+    L0->nnz = I.A0->nnz();
+    alloc_level_vectors(*L0, 0, s);
+    I.lv.push_back(std::move(L0));
+  }
+  std::vector<uint8_t> excl = I.exclude;
   double nnz_sum = 0.0;
-  const double nnz0 = (double)A0.nnz();
-  for (int l = 0;; ++l) {
-    std::unique_ptr<AmgLevel> L(new AmgLevel());
-    L->n = (int32_t)A->n_rows;
-    L->n_cols = (int32_t)A->n_cols;
-    L->nnz = A->nnz();
-    nnz_sum += (double)L->nnz;
-    if (l > 0) {
-      L->A.upload_pattern(*S, A->nnz());
-      L->diag_pos.upload(diag_positions(*A, *S, L->n));
-    }
-    L->dinv.alloc_zero(std::max(L->n, 1), s);
-    L->x.alloc_zero(std::max(L->n_cols, 1), s);
-    L->x2.alloc_zero(std::max(L->n_cols, 1), s);
-    L->r.alloc_zero(std::max(L->n, 1), s);
-    if (l > 0) L->b.alloc_zero(std::max(L->n, 1), s);
-    const bool stop = (L->n <= opt.coarse_size) || (l + 1 >= opt.max_levels);
+  for (size_t l = 0;; ++l) {
+    AmgLevel& L = *I.lv[l];
+    const HostCsr& A = (l == 0) ? *I.A0 : L.hA;
+    const HostSell& S = (l == 0) ? *I.S0 : L.hS;
+    const DevSell& dA = (l == 0) ? Afine : L.A;
+    nnz_sum += (double)A.nnz();
+    const bool stop = (L.n <= opt.coarse_size) || ((int)l + 1 >= opt.max_levels);
     std::vector<int32_t> agg;
     int32_t na = 0;
     if (!stop) {
-      na = aggregate(*A, L->n, excl, agg);
-      if (na <= 0 || na > 0.85 * L->n) na = 0;  // coarsening stalled
+      // strength of connection from the current values: |a_ij| >= theta_l sqrt(|a_ii a_jj|)
+      std::vector<uint8_t> strong;
+      const double theta = opt.strength_theta * std::pow(0.5, (double)l);
+      if (theta > 0) {
+        std::vector<double> v = dA.val.download(s);
+        std::vector<double> diag(L.n, 0.0);
+        for (int32_t i = 0; i < L.n; ++i)
+          for (int32_t k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k)
+            if (A.col[k] == i) diag[i] = std::fabs(v[S.pos(i, k - A.rowptr[i])]);
+        strong.assign(A.nnz(), 0);
+        for (int32_t i = 0; i < L.n; ++i)
+          for (int32_t k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k) {
+            const int32_t j = A.col[k];
+            if (j >= L.n || j == i) continue;
+            const double a = std::fabs(v[S.pos(i, k - A.rowptr[i])]);
+            strong[k] = (a >= theta * std::sqrt(diag[i] * diag[j])) && a > 0;
+          }
+      }
+      na = aggregate(A, L.n, excl, strong, agg);
+      if (na <= 0 || na > 0.85 * L.n) na = 0;  // coarsening stalled
     }
     if (stop || na == 0) {
-      L->last = true;
-      I.lv.push_back(std::move(L));
+      L.last = true;
+      numeric_level(I, l, Afine, fine_diag_pos);
       break;
     }
-    L->n_coarse = na;
-    HostCsr P = prolongator_pattern(*A, L->n, na, agg, opt.prolong_omega != 0.0);
+    L.n_coarse = na;
+    HostCsr P = prolongator_pattern(A, L.n, na, agg, opt.prolong_omega != 0.0);
     HostSell PS = sell_from_csr(P);
-    // pmap in A's SELL layout
     {
-      std::vector<uint8_t> pm(S->padded(), 255);
-      for (int32_t i = 0; i < L->n; ++i) {
+      std::vector<uint8_t> pm(S.padded(), 255);
+      for (int32_t i = 0; i < L.n; ++i) {
         const int32_t* pb = P.col.data() + P.rowptr[i];
         const int32_t* pe = P.col.data() + P.rowptr[i + 1];
         if (pb == pe) continue;
-        for (int32_t k = A->rowptr[i]; k < A->rowptr[i + 1]; ++k) {
-          const int32_t j = A->col[k];
-          if (j >= L->n || agg[j] < 0) continue;
+        for (int32_t k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k) {
+          const int32_t j = A.col[k];
+          if (j >= L.n || agg[j] < 0) continue;
           if (opt.prolong_omega == 0.0 && j != i) continue;
           const int32_t* q = std::lower_bound(pb, pe, agg[j]);
           const int64_t t = q - pb;
           if (t > 254) throw Error(SHAKTI_ERR_INVALID, "AMG: prolongator row too long");
-          pm[S->pos(i, k - A->rowptr[i])] = (uint8_t)t;
+          pm[S.pos(i, k - A.rowptr[i])] = (uint8_t)t;
         }
       }
-      L->pmap.upload(pm);
+      L.pmap.upload(pm);
     }
-    L->P.upload_pattern(PS, P.nnz());
+    L.P.upload_pattern(PS, P.nnz());
     std::vector<int32_t> tentry;
     HostCsr R = csr_transpose(P, &tentry);
     HostSell RS = sell_from_csr(R);
@@ -377,61 +564,62 @@ void Amg::setup(const HostCsr& A0, const HostSell& S0, const std::vector<uint8_t
       std::vector<int32_t> tm(RS.padded(), -1);
       for (int64_t r = 0; r < R.n_rows; ++r)
         for (int32_t k = R.rowptr[r]; k < R.rowptr[r + 1]; ++k) tm[RS.pos(r, k - R.rowptr[r])] = ppos[tentry[k]];
-      L->tmap.upload(tm);
+      L.tmap.upload(tm);
     }
-    L->R.upload_pattern(RS, R.nnz());
-    HostCsr AP = product_pattern(*A, P);
-    HostSell APS = sell_from_csr(AP);
-    L->AP.upload_pattern(APS, AP.nnz());
-    HostCsr Ac = product_pattern(R, AP);
-    Ac.n_cols = na;
-    I.lv.push_back(std::move(L));
-    Acur = std::move(Ac);
-    Scur = sell_from_csr(Acur);
-    A = &Acur;
-    S = &Scur;
+    L.R.upload_pattern(RS, R.nnz());
+    HostCsr AP = product_pattern(A, P);
+    L.AP.upload_pattern(sell_from_csr(AP), AP.nnz());
+    std::unique_ptr<AmgLevel> Ln(new AmgLevel());
+    Ln->hA = product_pattern(R, AP);
+    Ln->hA.n_cols = na;
+    Ln->hS = sell_from_csr(Ln->hA);
+    Ln->n = na;
+    Ln->n_cols = na;
+    Ln->nnz = Ln->hA.nnz();
+    Ln->A.upload_pattern(Ln->hS, Ln->hA.nnz());
+    Ln->diag_pos.upload(diag_positions(Ln->hA, Ln->hS, na));
+    alloc_level_vectors(*Ln, (int)l + 1, s);
+    I.lv.push_back(std::move(Ln));
+    numeric_level(I, l, Afine, fine_diag_pos);
     excl.clear();
   }
   AmgLevel& last = *I.lv.back();
-  I.dense_coarse = last.n <= 512 && I.lv.size() > 1 ? true : (last.n <= 512);
+  I.dense_coarse = last.n <= 512;
   if (I.dense_coarse) {
-    I.dense.alloc_zero((size_t)2 * last.n * last.n, s);
+    I.dense.alloc_zero(std::max<size_t>(1, (size_t)2 * last.n * last.n), s);
     I.info.alloc_zero(1, s);
   }
+  const double nnz0 = (double)I.A0->nnz();
   I.op_complexity = nnz0 > 0 ? nnz_sum / nnz0 : 0.0;
-  SHAKTI_CUDA(cudaStreamSynchronize(s));
+  I.built = true;
 }
 
-static void spgemm(const DevSell& A, const DevSell& B, DevSell& C, cudaStream_t s) {
-  SHAKTI_CUDA(cudaMemsetAsync(C.val.p, 0, sizeof(double) * C.padded, s));
-  if (A.n_rows == 0) return;
-  SHAKTI_LAUNCH(amg_spgemm_kernel, div_up(A.n_rows, 128), 128, 0, s, view(A), A.rowlen.p, view(B), B.rowlen.p,
-                B.n_rows, C.slice_ptr.p, C.col.p, C.rowlen.p, C.val.p);
+// Cheap per-solve update when the hierarchy itself is kept (lagged): the fine-level smoother must
+// match the CURRENT operator, so its diagonal is recomputed and its Chebyshev bound is set to the
+// (always safe) Gershgorin bound.  Coarse levels stay consistent among themselves.
+void Amg::refresh_fine_smoother(const DevSell& Afine, const int32_t* fine_diag_pos) {
+  Impl& I = *p_;
+  cudaStream_t s = I.s;
+  if (!I.built || I.lv.empty()) return;
+  AmgLevel& L = *I.lv[0];
+  if (L.n == 0) return;
+  SHAKTI_LAUNCH(amg_dinv_kernel, div_up(L.n, 256), 256, 0, s, L.n, fine_diag_pos, Afine.val.p, L.dinv.p);
+  if (I.opt.smoother != 1 || (L.last && I.dense_coarse)) return;
+  SHAKTI_CUDA(cudaMemsetAsync(I.scal.p + 1, 0, sizeof(double), s));
+  SHAKTI_LAUNCH(amg_gershgorin_kernel, div_up(L.n, 256), 256, 0, s, view(Afine), L.dinv.p,
+                reinterpret_cast<unsigned long long*>(I.scal.p + 1));
+  SHAKTI_CUDA(cudaMemcpyAsync(I.host_scal, I.scal.p + 1, sizeof(double), cudaMemcpyDeviceToHost, s));
+  SHAKTI_CUDA(cudaStreamSynchronize(s));
+  if (I.host_scal[0] > 0 && std::isfinite(I.host_scal[0])) L.lmax = I.host_scal[0];
 }
 
 void Amg::refresh(const DevSell& Afine, const int32_t* fine_diag_pos) {
   Impl& I = *p_;
   cudaStream_t s = I.s;
-  for (size_t l = 0; l < I.lv.size(); ++l) {
-    AmgLevel& L = *I.lv[l];
-    const DevSell& A = (l == 0) ? Afine : L.A;
-    const int32_t* dpos = (l == 0) ? fine_diag_pos : L.diag_pos.p;
-    if (L.n > 0) SHAKTI_LAUNCH(amg_dinv_kernel, div_up(L.n, 256), 256, 0, s, L.n, dpos, A.val.p, L.dinv.p);
-    if (L.last) break;
-    SHAKTI_CUDA(cudaMemsetAsync(L.P.val.p, 0, sizeof(double) * L.P.padded, s));
-    SHAKTI_LAUNCH(amg_prolongator_kernel, div_up(L.n, 256), 256, 0, s, view(A), L.pmap.p, dpos, L.dinv.p,
-                  I.opt.prolong_omega, L.P.slice_ptr.p, L.P.val.p);
-    SHAKTI_LAUNCH(amg_gather_vals_kernel, (int)std::min<int64_t>(148 * 8, std::max<int64_t>(1, (L.R.padded + 255) / 256)), 256, 0, s,
-                  L.R.padded, L.tmap.p, L.P.val.p, L.R.val.p);
-    // A restricted to its square block times P, then R * (AP)
-    {
-      DevSell& AP = L.AP;
-      SHAKTI_CUDA(cudaMemsetAsync(AP.val.p, 0, sizeof(double) * AP.padded, s));
-      SHAKTI_LAUNCH(amg_spgemm_kernel, div_up(L.n, 128), 128, 0, s, view(A), A.rowlen.p, view(L.P), L.P.rowlen.p,
-                    L.P.n_rows, AP.slice_ptr.p, AP.col.p, AP.rowlen.p, AP.val.p);
-    }
-    spgemm(L.R, L.AP, I.lv[l + 1]->A, s);
-  }
+  if (!I.built) build_hierarchy(I, Afine, fine_diag_pos);
+  else
+    for (size_t l = 0; l < I.lv.size(); ++l) numeric_level(I, l, Afine, fine_diag_pos);
+  update_smoother_bounds(I, Afine);
   if (I.dense_coarse) {
     AmgLevel& L = *I.lv.back();
     const DevSell& A = (I.lv.size() == 1) ? Afine : L.A;
@@ -446,51 +634,72 @@ void Amg::refresh(const DevSell& Afine, const int32_t* fine_diag_pos) {
   ++refreshes_;
 }
 
+// `sweeps` smoothing steps on A x = b, in place on L.x (ping-pong with L.x2).  zero_guess: L.x is
+// taken as 0 and the first step needs no SpMV.
+static void smooth(Amg::Impl& I, AmgLevel& L, const DevSell& A, const double* b, int sweeps, bool zero_guess) {
+  cudaStream_t s = I.s;
+  if (sweeps <= 0) {
+    if (zero_guess) launch_fill(L.n, 0.0, L.x.p, s);
+    return;
+  }
+  if (I.opt.smoother == 1) {   // Chebyshev polynomial of degree `sweeps` on D^-1 A, interval [lmax/ratio, lmax]
+    const double hi = L.lmax, lo = L.lmax / I.opt.cheby_ratio;
+    const double theta = 0.5 * (hi + lo), delta = 0.5 * (hi - lo), sigma = theta / delta;
+    double rho = 1.0 / sigma;
+    int k0 = 0;
+    if (zero_guess) {
+      SHAKTI_LAUNCH(amg_cheby_first_kernel, div_up(L.n, 256), 256, 0, s, L.n, L.dinv.p, b, 1.0 / theta, L.d.p, L.x.p);
+      k0 = 1;
+    }
+    for (int k = k0; k < sweeps; ++k) {
+      double c1, c2;
+      if (k == 0) { c1 = 0.0; c2 = 1.0 / theta; }
+      else {
+        const double rho_n = 1.0 / (2.0 * sigma - rho);
+        c1 = rho_n * rho;
+        c2 = 2.0 * rho_n / delta;
+        rho = rho_n;
+      }
+      SHAKTI_LAUNCH(amg_cheby_kernel, div_up((int64_t)A.n_slices * 32, 256), 256, 0, s, view(A), L.dinv.p, b, L.x.p, L.d.p,
+                    L.x2.p, c1, c2);
+      std::swap(L.x.p, L.x2.p);
+    }
+  } else {                      // damped Jacobi
+    const double om = I.opt.smoother_omega;
+    int k0 = 0;
+    if (zero_guess) { launch_pointwise_mul(L.n, L.dinv.p, b, om, L.x.p, s); k0 = 1; }
+    for (int k = k0; k < sweeps; ++k) {
+      launch_jacobi(view(A), L.dinv.p, b, L.x.p, L.x2.p, om, s);
+      std::swap(L.x.p, L.x2.p);
+    }
+  }
+}
+
 void Amg::apply(const DevSell& Afine, const double* rin, double* z) {
   Impl& I = *p_;
   cudaStream_t s = I.s;
-  const double om = I.opt.smoother_omega;
   const int nl = (int)I.lv.size();
-  // downward sweep
-  for (int l = 0; l < nl; ++l) {
+  for (int l = 0; l < nl; ++l) {   // downward
     AmgLevel& L = *I.lv[l];
     const DevSell& A = (l == 0) ? Afine : L.A;
     const double* b = (l == 0) ? rin : L.b.p;
     if (L.n == 0) continue;
     if (L.last) {
-      if (I.dense_coarse) {
-        SHAKTI_LAUNCH(amg_dense_apply_kernel, div_up((int64_t)L.n * 32, 128), 128, 0, s, L.n, I.dense.p, b, L.x.p);
-      } else {
-        // no dense solve available: a few damped-Jacobi sweeps
-        launch_pointwise_mul(L.n, L.dinv.p, b, om, L.x.p, s);
-        for (int k = 0; k < 8; ++k) {
-          launch_jacobi(view(A), L.dinv.p, b, L.x.p, L.x2.p, om, s);
-          std::swap(L.x.p, L.x2.p);
-        }
-      }
+      if (I.dense_coarse) SHAKTI_LAUNCH(amg_dense_apply_kernel, div_up((int64_t)L.n * 32, 128), 128, 0, s, L.n, I.dense.p, b, L.x.p);
+      else smooth(I, L, A, b, 8, true);
       break;
     }
-    // pre-smoothing from a zero guess: first sweep is a scaling
-    launch_pointwise_mul(L.n, L.dinv.p, b, om, L.x.p, s);
-    for (int k = 1; k < I.opt.presmooth; ++k) {
-      launch_jacobi(view(A), L.dinv.p, b, L.x.p, L.x2.p, om, s);
-      std::swap(L.x.p, L.x2.p);
-    }
-    if (I.opt.presmooth == 0) launch_fill(L.n, 0.0, L.x.p, s);
+    smooth(I, L, A, b, I.opt.presmooth, true);
     launch_residual(view(A), L.x.p, b, L.r.p, s);
     launch_spmv(view(L.R), L.r.p, I.lv[l + 1]->b.p, s);
   }
-  // upward sweep
-  for (int l = nl - 2; l >= 0; --l) {
+  for (int l = nl - 2; l >= 0; --l) {   // upward
     AmgLevel& L = *I.lv[l];
     const DevSell& A = (l == 0) ? Afine : L.A;
     const double* b = (l == 0) ? rin : L.b.p;
     if (L.n == 0) continue;
     launch_spmv_add(view(L.P), I.lv[l + 1]->x.p, L.x.p, s);
-    for (int k = 0; k < I.opt.postsmooth; ++k) {
-      launch_jacobi(view(A), L.dinv.p, b, L.x.p, L.x2.p, om, s);
-      std::swap(L.x.p, L.x2.p);
-    }
+    smooth(I, L, A, b, I.opt.postsmooth, false);
   }
   AmgLevel& L0 = *I.lv[0];
   if (L0.n) SHAKTI_CUDA(cudaMemcpyAsync(z, L0.x.p, sizeof(double) * L0.n, cudaMemcpyDeviceToDevice, s));

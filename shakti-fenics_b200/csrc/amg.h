@@ -18,19 +18,26 @@ struct AmgOptions {
   int presmooth = 1, postsmooth = 1;
   double smoother_omega = 0.67;
   double prolong_omega = 0.67;  // 0 => plain aggregation
+  double strength_theta = 0.08; // |a_ij| >= theta 0.5^level sqrt(|a_ii a_jj|) is a strong connection (0: all)
+  int smoother = 1;             // 0 damped Jacobi (presmooth/postsmooth sweeps), 1 Chebyshev (degree = sweeps)
+  double cheby_ratio = 5.0;     // Chebyshev interval [lmax/ratio, lmax] of D^-1 A
 };
 
 class Amg {
  public:
   Amg();
   ~Amg();
-  // Symbolic set-up from the fine pattern (rows x cols, cols >= rows; only the square
-  // rows x rows block is coarsened).  `exclude[i] != 0` rows (Dirichlet) stay out of the
-  // coarse space.  fine_diag_pos: SELL position of each row's diagonal.
+  // Register the fine pattern (rows x cols, cols >= rows; only the square rows x rows block is
+  // coarsened; A and S must outlive this object).  `exclude[i] != 0` rows (Dirichlet) stay out
+  // of the coarse space.  The hierarchy itself is built by the first refresh(), level by level:
+  // strength of connection needs the values, so host symbolic work and device numerics interleave.
   void setup(const HostCsr& A, const HostSell& S, const std::vector<uint8_t>& exclude, const AmgOptions& opt,
              int sm_count, cudaStream_t s);
   // Numeric phase: recompute P, R, coarse operators and smoother diagonals from the fine values.
   void refresh(const DevSell& Afine, const int32_t* fine_diag_pos);
+  // Per-solve update of the fine-level smoother only (diagonal + safe Chebyshev bound) for
+  // solves that reuse a lagged hierarchy.
+  void refresh_fine_smoother(const DevSell& Afine, const int32_t* fine_diag_pos);
   // z = M^-1 r : one V-cycle from a zero initial guess.  r: n rows; z: n_cols-long buffer
   // (entries beyond n rows are left untouched and must be zero / halo-free).
   void apply(const DevSell& Afine, const double* r, double* z);
@@ -39,8 +46,10 @@ class Amg {
   int64_t refreshes() const { return refreshes_; }
   bool ready() const { return refreshes_ > 0; }
 
- private:
+ public:
   struct Impl;
+
+ private:
   std::unique_ptr<Impl> p_;
   int64_t refreshes_ = 0;
 };

@@ -76,6 +76,10 @@ struct shakti_model {
   std::unique_ptr<Amg> amg;
   bool amg_setup_done = false;
   int64_t solves_since_refresh = 0;
+  int64_t step_of_refresh = -1000000;  // st.steps at the last AMG refresh
+  int newton_it_in_step = 0;           // Newton iteration index of the solve in progress
+  int its_after_refresh = 0;           // Krylov iterations of the first solve after the last refresh
+  int last_solve_its = 0;
   // Newton state
   double residual0 = 0.0;  // DOLFINx NewtonSolver::_residual0 (kept across solves)
   shakti_stats st{};
@@ -188,6 +192,9 @@ static void ensure_amg(shakti_model* m) {
   ao.postsmooth = m->opt.amg_postsmooth;
   ao.smoother_omega = m->opt.amg_smoother_omega;
   ao.prolong_omega = m->opt.amg_prolong_omega;
+  ao.strength_theta = m->opt.amg_strength_theta;
+  ao.cheby_ratio = m->opt.amg_cheby_ratio;
+  ao.smoother = m->opt.amg_smoother;
   std::vector<uint8_t> excl = m->isbc.download(m->stream);
   excl.resize(m->hm.n_owned);
   m->amg.reset(new Amg());
@@ -205,34 +212,60 @@ static KrylovResult linear_solve(shakti_model* m, const double* rhs, double* dx,
     m->halo.exchange(xl, m->stream);
     launch_spmv(Jv, xl, y, m->stream);
   };
-  PrecFn M;
-  if (m->opt.precond == SHAKTI_PC_JACOBI) {
-    launch_extract_dinv(no, m->diag_pos.p, m->J.val.p, m->dinv.p, m->stream);
-    M = [m, no](const double* r, double* z) { launch_pointwise_mul(no, m->dinv.p, r, 1.0, z, m->stream); };
-  } else if (m->opt.precond == SHAKTI_PC_AMG) {
+  AllReduceFn ar = [m](double* d, int c) { allreduce(m, d, c); };
+  auto krylov = [&](const PrecFn& M, int max_it) {
+    if (m->opt.linear_solver == SHAKTI_KSP_BICGSTAB) {
+      if (!m->bicg_init) { m->bicg.init(no, m->hm.n_local, m->sm_count, m->stream); m->bicg_init = true; }
+      return m->bicg.solve(A, M, ar, rhs, dx, rtol, m->opt.linear_atol, max_it);
+    }
+    return m->gmres.solve(A, M, ar, rhs, dx, rtol, m->opt.linear_atol, max_it);
+  };
+  KrylovResult r;
+  if (m->opt.precond == SHAKTI_PC_AMG) {
     ensure_amg(m);
+    // The hierarchy is a preconditioner only: its numbers are recomputed at the first Newton
+    // solve of every amg_refresh_every-th time step, or earlier when the Krylov iteration count
+    // has grown by more than half since the last refresh.  The Krylov solve always uses the
+    // current J, so a lagged hierarchy costs iterations, never accuracy; a solve that stalls on
+    // a lagged hierarchy is repeated once with a fresh one.
     const int every = std::max(1, m->opt.amg_refresh_every);
-    if (!m->amg->ready() || (m->solves_since_refresh % every) == 0) {
+    const bool due = m->newton_it_in_step == 0 && (m->st.steps - m->step_of_refresh) >= every;
+    const bool degraded = m->its_after_refresh > 0 && m->last_solve_its > (3 * m->its_after_refresh) / 2 + 2;
+    auto do_refresh = [&]() {
       m->amg->refresh(m->J, m->diag_pos.p);
       m->st.amg_refreshes++;
-    }
-    m->solves_since_refresh++;
-    M = [m](const double* r, double* z) { m->amg->apply(m->J, r, z); };
-  } else {
-    M = [m, no](const double* r, double* z) {
-      SHAKTI_CUDA(cudaMemcpyAsync(z, r, sizeof(double) * no, cudaMemcpyDeviceToDevice, m->stream));
+      m->step_of_refresh = m->st.steps;
+      m->its_after_refresh = -1;
     };
-  }
-  AllReduceFn ar = [m](double* d, int c) { allreduce(m, d, c); };
-  KrylovResult r;
-  if (m->opt.linear_solver == SHAKTI_KSP_BICGSTAB) {
-    if (!m->bicg_init) { m->bicg.init(no, m->hm.n_local, m->sm_count, m->stream); m->bicg_init = true; }
-    r = m->bicg.solve(A, M, ar, rhs, dx, rtol, m->opt.linear_atol, m->opt.linear_max_it);
+    bool fresh = false;
+    if (!m->amg->ready() || due || degraded) { do_refresh(); fresh = true; }
+    else m->amg->refresh_fine_smoother(m->J, m->diag_pos.p);
+    PrecFn M = [m](const double* rr, double* z) { m->amg->apply(m->J, rr, z); };
+    int budget = m->opt.linear_max_it;
+    if (!fresh && m->its_after_refresh > 0) budget = std::min(budget, 3 * m->its_after_refresh + 20);
+    r = krylov(M, budget);
+    m->st.linear_its += r.iterations;
+    if (!r.converged && !fresh) {
+      do_refresh();
+      r = krylov(M, m->opt.linear_max_it);
+      m->st.linear_its += r.iterations;
+    }
   } else {
-    r = m->gmres.solve(A, M, ar, rhs, dx, rtol, m->opt.linear_atol, m->opt.linear_max_it);
+    PrecFn M;
+    if (m->opt.precond == SHAKTI_PC_JACOBI) {
+      launch_extract_dinv(no, m->diag_pos.p, m->J.val.p, m->dinv.p, m->stream);
+      M = [m, no](const double* rr, double* z) { launch_pointwise_mul(no, m->dinv.p, rr, 1.0, z, m->stream); };
+    } else {
+      M = [m, no](const double* rr, double* z) {
+        SHAKTI_CUDA(cudaMemcpyAsync(z, rr, sizeof(double) * no, cudaMemcpyDeviceToDevice, m->stream));
+      };
+    }
+    r = krylov(M, m->opt.linear_max_it);
+    m->st.linear_its += r.iterations;
   }
-  m->st.linear_its += r.iterations;
   m->st.last_linear_relres = r.relres;
+  m->last_solve_its = r.iterations;
+  if (m->its_after_refresh < 0) m->its_after_refresh = std::max(1, r.iterations);
   return r;
 }
 
@@ -264,6 +297,7 @@ static void newton_solve(shakti_model* m, double dt, int32_t* niter, int32_t* co
     // The reference solves each Newton system exactly (LU).  Here the Krylov residual target is
     // linear_rtol relative to the residual the Newton solve STARTED from, so later iterations
     // (whose right-hand side is already small) are not over-solved.
+    m->newton_it_in_step = it;
     const double rtol_k = std::min(1e-2, m->opt.linear_rtol * std::max(1.0, r > 0 ? r_init / r : 1.0));
     KrylovResult kr = linear_solve(m, m->rhs.p, m->dx.p, rtol_k);
     if (!kr.converged)
@@ -533,8 +567,9 @@ int shakti_default_options(shakti_options* o) {
   o->newton_rtol = 1e-9; o->newton_atol = 1e-10; o->newton_max_it = 50; o->newton_r0 = SHAKTI_R0_INITIAL_RESIDUAL;
   o->linear_solver = SHAKTI_KSP_GMRES; o->precond = SHAKTI_PC_AMG;
   o->linear_rtol = 1e-12; o->linear_atol = 0.0; o->linear_max_it = 2000; o->gmres_restart = 40;
-  o->amg_refresh_every = 1; o->amg_max_levels = 12; o->amg_coarse_size = 128; o->amg_presmooth = 1; o->amg_postsmooth = 1;
-  o->amg_smoother_omega = 0.67; o->amg_prolong_omega = 0.67;
+  o->amg_refresh_every = 1; o->amg_max_levels = 12; o->amg_coarse_size = 128; o->amg_presmooth = 2; o->amg_postsmooth = 2;
+  o->amg_smoother_omega = 0.67; o->amg_prolong_omega = 0.67; o->amg_strength_theta = 0.08; o->amg_cheby_ratio = 5.0;
+  o->amg_smoother = 1; o->amg_reserved = 0;
   o->b_min = 1.0e-5; o->assembly_kernel = 1; o->reorder = 1;
   return SHAKTI_OK;
 }
@@ -639,7 +674,9 @@ int shakti_set_options(shakti_model* m, const shakti_options* opt) {
   const bool amg_changed = opt->amg_max_levels != m->opt.amg_max_levels || opt->amg_coarse_size != m->opt.amg_coarse_size ||
                            opt->amg_presmooth != m->opt.amg_presmooth || opt->amg_postsmooth != m->opt.amg_postsmooth ||
                            opt->amg_smoother_omega != m->opt.amg_smoother_omega ||
-                           opt->amg_prolong_omega != m->opt.amg_prolong_omega;
+                           opt->amg_prolong_omega != m->opt.amg_prolong_omega ||
+                           opt->amg_strength_theta != m->opt.amg_strength_theta ||
+                           opt->amg_cheby_ratio != m->opt.amg_cheby_ratio || opt->amg_smoother != m->opt.amg_smoother;
   SHAKTI_REQUIRE(opt->reorder == m->opt.reorder, "reorder can only be chosen at create time");
   const int restart_old = m->opt.gmres_restart;
   m->opt = *opt;
@@ -731,6 +768,8 @@ int shakti_linear_solve(shakti_model* m, const double* rhs, double* dx, int32_t*
   scatter_in(m, m->stage.p, m->b2.p);
   // interior system: Dirichlet rows are identity
   launch_xmy_masked(m->hm.n_owned, m->b2.p, m->isbc.p, m->rhs.p, m->stream);
+  m->newton_it_in_step = 0;
+  m->step_of_refresh = -1000000;   // parity hook: always refresh
   KrylovResult r = linear_solve(m, m->rhs.p, m->dx.p, m->opt.linear_rtol);
   if (m->n_bc)
     SHAKTI_LAUNCH(fix_bc_dx_kernel, div_up(m->hm.n_owned, 256), 256, 0, m->stream, m->hm.n_owned, m->isbc.p, m->b2.p, m->dx.p);

@@ -45,6 +45,8 @@ class Options(C.Structure):
         ("amg_refresh_every", C.c_int32), ("amg_max_levels", C.c_int32),
         ("amg_coarse_size", C.c_int32), ("amg_presmooth", C.c_int32), ("amg_postsmooth", C.c_int32),
         ("amg_smoother_omega", C.c_double), ("amg_prolong_omega", C.c_double),
+        ("amg_strength_theta", C.c_double), ("amg_cheby_ratio", C.c_double),
+        ("amg_smoother", C.c_int32), ("amg_reserved", C.c_int32),
         ("b_min", C.c_double), ("assembly_kernel", C.c_int32), ("reorder", C.c_int32),
     ]
 
@@ -126,6 +128,8 @@ def _apply_options(o, kw):
             v = PC[v]
         if k == "newton_r0" and isinstance(v, str):
             v = NEWTON_R0[v]
+        if k == "amg_smoother" and isinstance(v, str):
+            v = dict(jacobi=0, chebyshev=1)[v]
         setattr(o, k, v)
 
 

@@ -177,3 +177,18 @@ def test_newton_failure_is_reported():
         assert e.value.code == capi.ERR_NOT_CONVERGED
     finally:
         m.close()
+
+
+def test_multi_gpu_partitioned_run_matches_oracle():
+    """Real NCCL run on 2 GPUs of this box (skipped when fewer are visible)."""
+    import subprocess
+    import sys
+    import torch
+    from pathlib import Path
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = Path(__file__).with_name("multi_gpu_check.py")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29517", str(script)],
+                       capture_output=True, text=True, timeout=600)
+    assert "MULTI_GPU_CHECK PASSED" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
