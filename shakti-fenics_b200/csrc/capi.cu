@@ -2,6 +2,7 @@
 // Newton loop, the time step and the parity hooks.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 
@@ -55,6 +56,11 @@ struct shakti_model {
   // device mesh
   DevBuf<double> x, y;
   DevBuf<int32_t> c0, c1, c2, slot, diag_pos, win, l2g;
+  // row-block assembly plan (prep.h AssemblyBlocks)
+  AssemblyBlocks ab;
+  DevBuf<int32_t> ab_eptr, ab_elems, ab_incptr, ab_hptr, ab_halo;
+  DevBuf<uint16_t> ab_inc, ab_lv;
+  DevBuf<uint32_t> ab_src;
   // vertex fields (n_local)
   DevBuf<double> z_b, z_s, h0, G, inputs, storage, b, b2, N, N_n, qx, qy, melt, melt2, F, dx, rhs, dinv;
   DevBuf<double> kbar;
@@ -175,6 +181,14 @@ static void compute_kbar(shakti_model* m) {
 static void assemble(shakti_model* m, double dt, int want_J) {
   refresh_h0(m);
   const int32_t no = m->hm.n_owned;
+  if (m->opt.assembly_kernel == 0 && m->ab.ok) {
+    AssemblyPlanView pl{no, m->ab.rows_per_block, m->ab.n_blocks, m->ab.max_cells, m->ab.max_verts, m->ab_eptr.p,
+                        m->ab_elems.p, m->ab_lv.p, m->ab_hptr.p, m->ab_halo.p, m->ab_incptr.p, m->ab_inc.p, m->ab_src.p};
+    launch_assemble_blocks(pl, m->fields(), m->kbar.p, dt, m->N_bdry, m->J.slice_ptr.p, m->F.p, m->J.val.p, want_J,
+                           m->dprm, m->stream);
+    if (want_J) m->J_valid = true;
+    return;
+  }
   SHAKTI_CUDA(cudaMemsetAsync(m->F.p, 0, sizeof(double) * no, m->stream));
   if (want_J) SHAKTI_CUDA(cudaMemsetAsync(m->J.val.p, 0, sizeof(double) * m->J.padded, m->stream));
   launch_assemble_atomic(m->hm.ne, no, m->c0.p, m->c1.p, m->c2.p, m->slot.p, m->fields(), m->kbar.p, dt,
@@ -410,6 +424,27 @@ static void create(int64_t nv, int64_t ne, const double* xy, const int32_t* cell
     m->c0.upload(a); m->c1.upload(b); m->c2.upload(c);
   }
   m->slot.upload(hm.slot);
+  {
+    const char* env = getenv("SHAKTI_ASM_MAX_CELLS");   // tuning knob: smaller => fewer rows per block
+    build_assembly_blocks(hm, env ? atoi(env) : 800, m->ab);
+  }
+  if (false) build_assembly_blocks(hm, 800, m->ab);      // <= 800 cells per block: 77 KB of staged cell data + ~35 KB of vertex data
+  if (m->ab.ok) {
+    m->ab_eptr.upload(m->ab.blk_eptr);
+    m->ab_elems.upload(m->ab.blk_elems);
+    m->ab_incptr.upload(m->ab.inc_ptr);
+    m->ab_inc.upload(m->ab.inc_code);
+    m->ab_src.upload(m->ab.src);
+    m->ab_lv.upload(m->ab.blk_lv);
+    m->ab_hptr.upload(m->ab.blk_hptr);
+    m->ab_halo.upload(m->ab.blk_halo);
+    std::vector<uint16_t>().swap(m->ab.blk_lv);
+    std::vector<int32_t>().swap(m->ab.blk_halo);
+    // host copies are only needed for the plan itself
+    std::vector<int32_t>().swap(m->ab.blk_elems);
+    std::vector<uint16_t>().swap(m->ab.inc_code);
+    std::vector<uint32_t>().swap(m->ab.src);
+  }
   m->diag_pos.upload(hm.diag_pos);
   m->win.upload(hm.win);
   m->l2g.upload(hm.l2g);
@@ -570,7 +605,7 @@ int shakti_default_options(shakti_options* o) {
   o->amg_refresh_every = 1; o->amg_max_levels = 12; o->amg_coarse_size = 128; o->amg_presmooth = 2; o->amg_postsmooth = 2;
   o->amg_smoother_omega = 0.67; o->amg_prolong_omega = 0.67; o->amg_strength_theta = 0.08; o->amg_cheby_ratio = 5.0;
   o->amg_smoother = 1; o->amg_reserved = 0;
-  o->b_min = 1.0e-5; o->assembly_kernel = 1; o->reorder = 1;
+  o->b_min = 1.0e-5; o->assembly_kernel = 0; o->reorder = 1;
   return SHAKTI_OK;
 }
 

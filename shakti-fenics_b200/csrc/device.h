@@ -10,6 +10,7 @@ struct DevParams {
   double g, rho_i, rho_w, nu, Lh, omega, n, A;
   double cm;    // 1/rho_i - 1/rho_w
   double rwg;   // rho_w * g
+  double inv_rwg, inv_Lh, cm_over_Lh;   // reciprocals, so the cell kernels do not divide by constants
   int n_is_3;   // Glen exponent is exactly 3 => closure terms are polynomials
 };
 
@@ -50,6 +51,16 @@ void launch_assemble_atomic(int32_t ne, int32_t n_owned, const int32_t* c0, cons
                             const int32_t* c2, const int32_t* slot, FieldPtrs f, const double* kbar,
                             double dt, double N_bdry, double* F, double* Jval, int want_J,
                             DevParams p, cudaStream_t s);
+struct AssemblyPlanView {   // device arrays of prep.h AssemblyBlocks
+  int32_t n_owned, rows_per_block, n_blocks, cap, vcap;
+  const int32_t *blk_eptr, *blk_elems;
+  const uint16_t* blk_lv;
+  const int32_t *blk_hptr, *blk_halo, *inc_ptr;
+  const uint16_t* inc_code;
+  const uint32_t* src;
+};
+void launch_assemble_blocks(const AssemblyPlanView& plan, FieldPtrs f, const double* kbar, double dt, double N_bdry,
+                            const int32_t* slice_ptr, double* F, double* Jval, int want_J, DevParams p, cudaStream_t s);
 void launch_apply_bc(int32_t n_owned, const uint8_t* isbc, const double* N, double N_bdry,
                      const int32_t* diag_pos, double* F, double* Jval, int want_J, cudaStream_t s);
 

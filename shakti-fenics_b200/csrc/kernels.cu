@@ -14,6 +14,9 @@ DevParams make_dev_params(const shakti_params& p) {
   d.omega = p.omega; d.n = p.n; d.A = p.A;
   d.cm = 1.0 / p.rho_i - 1.0 / p.rho_w;
   d.rwg = p.rho_w * p.g;
+  d.inv_rwg = 1.0 / d.rwg;
+  d.inv_Lh = 1.0 / p.Lh;
+  d.cm_over_Lh = d.cm / p.Lh;
   d.n_is_3 = (p.n == 3.0);
   return d;
 }
@@ -134,21 +137,10 @@ struct ElemOut {
   double J[3][3];
 };
 
-__device__ __forceinline__ void element_FJ(const int32_t v[3], const FieldPtrs& f, double kb, double dt,
-                                           const DevParams& p, ElemOut& o, double Nv[3]) {
-  const Geo g = geometry(f.x[v[0]], f.y[v[0]], f.x[v[1]], f.y[v[1]], f.x[v[2]], f.y[v[2]]);
-  double h[3], bb[3], mm[3], qxv[3], qyv[3], Nn[3], st[3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    Nv[i] = f.N[v[i]];
-    h[i] = f.h0[v[i]] - Nv[i] / p.rwg;
-    bb[i] = f.b[v[i]];
-    mm[i] = f.melt[v[i]];
-    qxv[i] = f.qx[v[i]];
-    qyv[i] = f.qy[v[i]];
-    Nn[i] = f.N_n[v[i]];
-    st[i] = f.storage[v[i]];
-  }
+__device__ __forceinline__ void element_core(const Geo& g, const double h[3], const double bb[3], const double mm[3],
+                                             const double qxv[3], const double qyv[3], const double Nv[3],
+                                             const double Nn[3], const double st[3], const double Gv[3],
+                                             const double inp[3], double kb, double dt, const DevParams& p, ElemOut& o) {
   double ghx = 0, ghy = 0, gbx = 0, gby = 0, gmx = 0, gmy = 0;
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
@@ -163,16 +155,16 @@ __device__ __forceinline__ void element_FJ(const int32_t v[3], const FieldPtrs& 
   double rl[3], rsum = 0, qxs = 0, qys = 0;
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    const double m0 = (f.G[v[i]] - p.rwg * (qxv[i] * ghx + qyv[i] * ghy)) / p.Lh;   // constitutive.py:25
+    const double m0 = (Gv[i] - p.rwg * (qxv[i] * ghx + qyv[i] * ghy)) * p.inv_Lh;   // constitutive.py:25
     const double md = (gb2 * mm[i] + bb[i] * gmgb) * inv1;                           // constitutive.py:26
-    rl[i] = p.cm * (m0 + md) - f.inputs[v[i]];
+    rl[i] = p.cm * (m0 + md) - inp[i];
     rsum += rl[i];
     qxs += qxv[i];
     qys += qyv[i];
   }
   const double m24 = g.detabs * (1.0 / 24.0);
-  const double kJ = -kb / p.rwg;
-  const double cadv = p.cm / p.Lh * m24;
+  const double kJ = -kb * p.inv_rwg;
+  const double cadv = p.cm_over_Lh * m24;
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     o.F[a] = kb * (ghx * g.gx[a] + ghy * g.gy[a]) + m24 * (rsum + rl[a]);
@@ -182,7 +174,7 @@ __device__ __forceinline__ void element_FJ(const int32_t v[3], const FieldPtrs& 
       o.J[a][b] = kJ * (g.gx[a] * g.gx[b] + g.gy[a] * g.gy[b]) + qax * g.gx[b] + qay * g.gy[b];
   }
   // closure + storage by quadrature
-  const double cs = 1.0 / (p.rwg * dt);
+  const double cs = p.inv_rwg / dt;
   const double e1 = p.n - 1.0, e2 = p.n - 2.0;
   double f0 = 0, f1 = 0, f2 = 0, m00 = 0, m01 = 0, m02 = 0, m11 = 0, m12 = 0, m22 = 0;
   const int nq = c_nrq;
@@ -217,6 +209,27 @@ __device__ __forceinline__ void element_FJ(const int32_t v[3], const FieldPtrs& 
   o.J[2][0] -= m02; o.J[2][1] -= m12; o.J[2][2] -= m22;
 }
 
+// vertex data gathered straight from global memory (cell-parallel variant)
+__device__ __forceinline__ void element_FJ(const int32_t v[3], const FieldPtrs& f, double kb, double dt,
+                                           const DevParams& p, ElemOut& o, double Nv[3]) {
+  const Geo g = geometry(f.x[v[0]], f.y[v[0]], f.x[v[1]], f.y[v[1]], f.x[v[2]], f.y[v[2]]);
+  double h[3], bb[3], mm[3], qxv[3], qyv[3], Nn[3], st[3], Gv[3], inp[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    Nv[i] = f.N[v[i]];
+    h[i] = f.h0[v[i]] - Nv[i] * p.inv_rwg;
+    bb[i] = f.b[v[i]];
+    mm[i] = f.melt[v[i]];
+    qxv[i] = f.qx[v[i]];
+    qyv[i] = f.qy[v[i]];
+    Nn[i] = f.N_n[v[i]];
+    st[i] = f.storage[v[i]];
+    Gv[i] = f.G[v[i]];
+    inp[i] = f.inputs[v[i]];
+  }
+  element_core(g, h, bb, mm, qxv, qyv, Nv, Nn, st, Gv, inp, kb, dt, p, o);
+}
+
 // Dirichlet lifting (scale -1: F += J_full (g - x) on bc columns) applied in place.
 __device__ __forceinline__ void apply_lifting(ElemOut& o, const double Nv[3], const bool bc[3], double N_bdry) {
 #pragma unroll
@@ -226,6 +239,30 @@ __device__ __forceinline__ void apply_lifting(ElemOut& o, const double Nv[3], co
 #pragma unroll
       for (int a = 0; a < 3; ++a) o.F[a] += o.J[a][b] * gx;
     }
+}
+
+// Same element computation with the vertex data already staged in shared memory
+// (sV[field][vcap], field order of enum VX..VI below; VH holds the head h, not h0).
+__device__ __forceinline__ void element_FJ_staged(const int v[3], const double* __restrict__ sV, int vcap, double kb,
+                                                  double dt, const DevParams& p, ElemOut& o, double Nv[3]) {
+  const Geo g = geometry(sV[0 * vcap + v[0]], sV[1 * vcap + v[0]], sV[0 * vcap + v[1]], sV[1 * vcap + v[1]],
+                         sV[0 * vcap + v[2]], sV[1 * vcap + v[2]]);
+  double h[3], bb[3], mm[3], qxv[3], qyv[3], Nn[3], st[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    h[i] = sV[2 * vcap + v[i]];
+    Nv[i] = sV[3 * vcap + v[i]];
+    Nn[i] = sV[4 * vcap + v[i]];
+    bb[i] = sV[5 * vcap + v[i]];
+    qxv[i] = sV[6 * vcap + v[i]];
+    qyv[i] = sV[7 * vcap + v[i]];
+    mm[i] = sV[9 * vcap + v[i]];
+    st[i] = sV[10 * vcap + v[i]];
+  }
+  double Gv[3], inp[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { Gv[i] = sV[8 * vcap + v[i]]; inp[i] = sV[11 * vcap + v[i]]; }
+  element_core(g, h, bb, mm, qxv, qyv, Nv, Nn, st, Gv, inp, kb, dt, p, o);
 }
 
 // Variant 1: one thread per cell, scatter with fp64 atomics into the SELL value array through
@@ -263,6 +300,117 @@ void launch_assemble_atomic(int32_t ne, int32_t n_owned, const int32_t* c0, cons
   if (ne == 0) return;
   SHAKTI_LAUNCH(assemble_atomic_kernel, div_up(ne, 128), 128, 0, s, ne, n_owned, c0, c1, c2, slot, f, kbar,
                 dt, N_bdry, F, Jval, want_J, p);
+}
+
+// Variant 0 (default): atomics-free row-block assembly.  A CUDA block owns a run of consecutive
+// rows (= whole SELL slices).
+//   Phase 0: the twelve vertex fields of the block's vertices (its own rows: contiguous, fully
+//            coalesced; plus the few halo vertices of its cells) are staged in shared memory.
+//   Phase 1: every cell touching those rows is computed from shared memory and its 3 + 9
+//            numbers are staged in shared memory (structure of arrays, conflict free).  Cells on
+//            block borders are computed by each block that needs them (~19 % extra at 256 rows).
+//   Phase 2: one thread per row gathers -- the residual and the diagonal from the row's incident
+//            cells, every off-diagonal entry from the (at most two) cells sharing that edge -- and
+//            writes the SELL values with plain coalesced stores.
+// No zero-fill, no atomics, bitwise reproducible.
+enum { VX = 0, VY, VH, VN, VNN, VB, VQX, VQY, VG, VM, VS, VI, VFIELDS };
+
+__global__ void __launch_bounds__(256, 2)
+assemble_blocks_kernel(int32_t n_owned, int32_t rows_per_block, int32_t cap, int32_t vcap,
+                       const int32_t* __restrict__ blk_eptr, const int32_t* __restrict__ blk_elems,
+                       const uint16_t* __restrict__ blk_lv, const int32_t* __restrict__ blk_hptr,
+                       const int32_t* __restrict__ blk_halo, const int32_t* __restrict__ inc_ptr,
+                       const uint16_t* __restrict__ inc_code, const uint32_t* __restrict__ src, FieldPtrs f,
+                       const double* __restrict__ kbar, double dt, double N_bdry, const int32_t* __restrict__ slice_ptr,
+                       double* __restrict__ F, double* __restrict__ Jval, int want_J, DevParams p) {
+  extern __shared__ double smem[];
+  double* sV = smem;                         // [VFIELDS][vcap]
+  double* sK = smem + (size_t)VFIELDS * vcap;  // [12][cap]: F0..F2, J00..J22
+  uint8_t* sBC = reinterpret_cast<uint8_t*>(sK + (size_t)12 * cap);   // [vcap]
+  const int32_t r0 = blockIdx.x * rows_per_block;
+  const int32_t nrows = min(rows_per_block, n_owned - r0);
+  const int32_t h0 = blk_hptr[blockIdx.x], nh = blk_hptr[blockIdx.x + 1] - h0;
+  // ---- phase 0
+  for (int32_t i = threadIdx.x; i < nrows + nh; i += blockDim.x) {
+    const int32_t g = i < nrows ? r0 + i : blk_halo[h0 + i - nrows];
+    const double Ni = f.N[g];
+    sV[VX * vcap + i] = f.x[g];
+    sV[VY * vcap + i] = f.y[g];
+    sV[VH * vcap + i] = f.h0[g] - Ni * p.inv_rwg;   // Head (constitutive.py:6-9)
+    sV[VN * vcap + i] = Ni;
+    sV[VNN * vcap + i] = f.N_n[g];
+    sV[VB * vcap + i] = f.b[g];
+    sV[VQX * vcap + i] = f.qx[g];
+    sV[VQY * vcap + i] = f.qy[g];
+    sV[VG * vcap + i] = f.G[g];
+    sV[VM * vcap + i] = f.melt[g];
+    sV[VS * vcap + i] = f.storage[g];
+    sV[VI * vcap + i] = f.inputs[g];
+    sBC[i] = f.isbc[g];
+  }
+  __syncthreads();
+  // ---- phase 1
+  const int32_t e0 = blk_eptr[blockIdx.x], e1 = blk_eptr[blockIdx.x + 1];
+  for (int32_t le = threadIdx.x; le < e1 - e0; le += blockDim.x) {
+    const int32_t e = blk_elems[e0 + le];
+    const uint16_t* lv = blk_lv + 3 * (size_t)(e0 + le);
+    const int v[3] = {lv[0], lv[1], lv[2]};
+    ElemOut o;
+    double Nv[3];
+    element_FJ_staged(v, sV, vcap, kbar[e], dt, p, o, Nv);
+    const bool bc[3] = {sBC[v[0]] != 0, sBC[v[1]] != 0, sBC[v[2]] != 0};
+    apply_lifting(o, Nv, bc, N_bdry);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      sK[a * cap + le] = o.F[a];
+#pragma unroll
+      for (int b = 0; b < 3; ++b) sK[(3 + 3 * a + b) * cap + le] = (bc[a] || bc[b]) ? 0.0 : o.J[a][b];
+    }
+  }
+  __syncthreads();
+  // ---- phase 2
+  if ((int32_t)threadIdx.x >= nrows) return;
+  const int32_t row = r0 + threadIdx.x;
+  const bool rbc = sBC[threadIdx.x] != 0;
+  double Fr = 0.0, Jd = 0.0;
+  for (int32_t k = inc_ptr[row]; k < inc_ptr[row + 1]; ++k) {
+    const uint32_t code = inc_code[k];
+    const uint32_t le = code >> 2, a = code & 3u;
+    Fr += sK[a * cap + le];
+    Jd += sK[(3 + 4 * a) * cap + le];
+  }
+  F[row] = rbc ? sV[VN * vcap + threadIdx.x] - N_bdry : Fr;
+  if (!want_J) return;
+  const int32_t slice = row >> 5;
+  const int32_t base = slice_ptr[slice];
+  const int32_t w = (slice_ptr[slice + 1] - base) >> 5;
+  for (int k = 0; k < w; ++k) {
+    const int32_t pos = base + 32 * k + (row & 31);
+    const uint32_t s2 = src[pos];
+    if (s2 == 0xFFFFFFFFu) continue;       // padding
+    double v;
+    if (s2 == 0xFFFEFFFEu) v = rbc ? 1.0 : Jd;
+    else {
+      const uint32_t ca = s2 & 0xFFFFu, cb = s2 >> 16;
+      v = sK[(3 + (ca & 15u)) * cap + (ca >> 4)];
+      if (cb != 0xFFFFu) v += sK[(3 + (cb & 15u)) * cap + (cb >> 4)];
+    }
+    Jval[pos] = v;
+  }
+}
+
+void launch_assemble_blocks(const AssemblyPlanView& pl, FieldPtrs f, const double* kbar, double dt, double N_bdry,
+                            const int32_t* slice_ptr, double* F, double* Jval, int want_J, DevParams p, cudaStream_t s) {
+  if (pl.n_blocks == 0) return;
+  const size_t smem = ((size_t)VFIELDS * pl.vcap + (size_t)12 * pl.cap) * sizeof(double) + pl.vcap;
+  static size_t configured = 0;
+  if (smem > configured) {
+    SHAKTI_CUDA(cudaFuncSetAttribute(assemble_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  SHAKTI_LAUNCH(assemble_blocks_kernel, pl.n_blocks, 256, smem, s, pl.n_owned, pl.rows_per_block, pl.cap, pl.vcap,
+                pl.blk_eptr, pl.blk_elems, pl.blk_lv, pl.blk_hptr, pl.blk_halo, pl.inc_ptr, pl.inc_code, pl.src, f, kbar, dt,
+                N_bdry, slice_ptr, F, Jval, want_J, p);
 }
 
 // F[bc] = N[bc] - g ; J[bc,bc] = 1  (DOLFINx set_bc with scale -1 / insert_diagonal)

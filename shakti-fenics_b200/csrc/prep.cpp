@@ -173,6 +173,107 @@ std::vector<int32_t> locate_dirichlet_dofs(int64_t nv, int64_t ne, const int32_t
   return out;
 }
 
+// ------------------------------------------------------------------ assembly row blocks
+
+void build_assembly_blocks(const HostMesh& m, int32_t max_cells_per_block, AssemblyBlocks& out) {
+  const int32_t no = m.n_owned, ne = m.ne;
+  // vertex -> (cell, local index) incidence of owned rows, cells ascending
+  std::vector<int32_t> vptr(no + 1, 0);
+  for (int32_t e = 0; e < ne; ++e)
+    for (int a = 0; a < 3; ++a) {
+      const int32_t r = m.cells[3 * (size_t)e + a];
+      if (r < no) vptr[r + 1]++;
+    }
+  for (int32_t r = 0; r < no; ++r) vptr[r + 1] += vptr[r];
+  std::vector<int32_t> vinc(vptr[no]);   // e*4 + a
+  {
+    std::vector<int32_t> fill(vptr.begin(), vptr.end() - 1);
+    for (int32_t e = 0; e < ne; ++e)
+      for (int a = 0; a < 3; ++a) {
+        const int32_t r = m.cells[3 * (size_t)e + a];
+        if (r < no) vinc[fill[r]++] = e * 4 + a;
+      }
+  }
+  std::vector<int32_t> stamp(ne, -1), lidx(ne, 0);
+  for (int32_t rb : {256, 128, 64, 32}) {
+    out = AssemblyBlocks();
+    std::fill(stamp.begin(), stamp.end(), -1);
+    out.rows_per_block = rb;
+    out.n_blocks = (no + rb - 1) / rb;
+    out.blk_eptr.assign(out.n_blocks + 1, 0);
+    out.blk_hptr.assign(out.n_blocks + 1, 0);
+    out.inc_ptr.assign(no + 1, 0);
+    out.inc_code.clear();
+    out.src.assign(m.S.padded(), 0xFFFFFFFFu);
+    bool fits = true, manifold = true;
+    std::vector<int32_t> elems, halo;
+    for (int32_t B = 0; B < out.n_blocks && fits; ++B) {
+      const int32_t r0 = B * rb, r1 = std::min(no, r0 + rb);
+      elems.clear();
+      for (int32_t r = r0; r < r1; ++r)
+        for (int32_t k = vptr[r]; k < vptr[r + 1]; ++k) {
+          const int32_t e = vinc[k] >> 2;
+          if (stamp[e] != B) { stamp[e] = B; elems.push_back(e); }
+        }
+      std::sort(elems.begin(), elems.end());
+      if ((int32_t)elems.size() > max_cells_per_block || elems.size() >= 4096) { fits = false; break; }
+      for (size_t i = 0; i < elems.size(); ++i) lidx[elems[i]] = (int32_t)i;
+      out.max_cells = std::max<int32_t>(out.max_cells, (int32_t)elems.size());
+      out.blk_elems.insert(out.blk_elems.end(), elems.begin(), elems.end());
+      out.blk_eptr[B + 1] = (int32_t)out.blk_elems.size();
+      // vertices of the block: its own rows first, then the other vertices of its cells (ascending)
+      halo.clear();
+      for (int32_t e : elems)
+        for (int a = 0; a < 3; ++a) {
+          const int32_t v = m.cells[3 * (size_t)e + a];
+          if (v < r0 || v >= r1) halo.push_back(v);
+        }
+      std::sort(halo.begin(), halo.end());
+      halo.erase(std::unique(halo.begin(), halo.end()), halo.end());
+      if ((size_t)(r1 - r0) + halo.size() >= 65535) { fits = false; break; }
+      out.max_verts = std::max<int32_t>(out.max_verts, (int32_t)((r1 - r0) + halo.size()));
+      for (int32_t e : elems)
+        for (int a = 0; a < 3; ++a) {
+          const int32_t v = m.cells[3 * (size_t)e + a];
+          uint16_t lv;
+          if (v >= r0 && v < r1) lv = (uint16_t)(v - r0);
+          else lv = (uint16_t)((r1 - r0) + (std::lower_bound(halo.begin(), halo.end(), v) - halo.begin()));
+          out.blk_lv.push_back(lv);
+        }
+      out.blk_halo.insert(out.blk_halo.end(), halo.begin(), halo.end());
+      out.blk_hptr[B + 1] = (int32_t)out.blk_halo.size();
+      for (int32_t r = r0; r < r1; ++r) {
+        for (int32_t k = vptr[r]; k < vptr[r + 1]; ++k)
+          out.inc_code.push_back((uint16_t)(lidx[vinc[k] >> 2] * 4 + (vinc[k] & 3)));
+        out.inc_ptr[r + 1] = (int32_t)out.inc_code.size();
+        // Jacobian entries of row r
+        for (int32_t kk = m.A.rowptr[r]; kk < m.A.rowptr[r + 1]; ++kk) {
+          const int32_t c = m.A.col[kk];
+          const int64_t p = m.S.pos(r, kk - m.A.rowptr[r]);
+          if (c == r) { out.src[p] = 0xFFFEFFFEu; continue; }
+          uint32_t codes[2] = {0xFFFFu, 0xFFFFu};
+          int found = 0;
+          for (int32_t k = vptr[r]; k < vptr[r + 1]; ++k) {
+            const int32_t e = vinc[k] >> 2, a = vinc[k] & 3;
+            for (int b = 0; b < 3; ++b)
+              if (m.cells[3 * (size_t)e + b] == c) {
+                if (found < 2) codes[found] = (uint32_t)(lidx[e] * 16 + 3 * a + b);
+                ++found;
+              }
+          }
+          if (found > 2) manifold = false;
+          out.src[p] = codes[0] | (codes[1] << 16);
+        }
+      }
+    }
+    if (fits) {
+      out.ok = manifold;
+      return;
+    }
+  }
+  out.ok = false;
+}
+
 // ------------------------------------------------------------------ Morton ordering
 
 static inline uint64_t spread_bits(uint64_t v) {  // 21 bits -> every 2nd bit

@@ -59,6 +59,26 @@ struct HostMesh {
   std::vector<Neighbor> nbrs;
 };
 
+// Row-block plan of the atomics-free assembly: a CUDA block owns `rows_per_block` consecutive
+// owned rows, computes every cell touching them into shared memory (cells on block borders are
+// computed by each block that needs them) and then GATHERS: each row sums its incident cells'
+// residual entries, each Jacobian entry the (at most two) cells containing its edge.
+struct AssemblyBlocks {
+  int32_t rows_per_block = 0, n_blocks = 0, max_cells = 0;
+  bool ok = false;                  // false: mesh not edge-manifold -> use the atomic kernel
+  int32_t max_verts = 0;            // most vertices (owned rows + halo) any block touches
+  std::vector<int32_t> blk_eptr;    // n_blocks + 1
+  std::vector<int32_t> blk_elems;   // local cell ids, ascending inside a block
+  std::vector<uint16_t> blk_lv;     // 3 per block cell: block-local vertex index (row - r0, or rows_in_block + halo position)
+  std::vector<int32_t> blk_hptr;    // n_blocks + 1: halo vertex lists
+  std::vector<int32_t> blk_halo;    // local vertex ids outside the block's own rows, ascending
+  std::vector<int32_t> inc_ptr;     // n_owned + 1
+  std::vector<uint16_t> inc_code;   // (cell index in block) * 4 + local vertex index
+  std::vector<uint32_t> src;        // per padded SELL entry: two 16-bit codes (cell index in block)*16 + 3a+b;
+                                    // 0xFFFF = none; diagonal entries hold 0xFFFEFFFE (use the incident list)
+};
+void build_assembly_blocks(const HostMesh& m, int32_t max_cells_per_block, AssemblyBlocks& out);
+
 // Build the rank-local mesh.  `reorder` = 1: Morton ordering of vertices; 0: caller order.
 void build_host_mesh(int64_t nv, int64_t ne, const double* xy, const int32_t* cells, int rank,
                      int nranks, int reorder, HostMesh& out);

@@ -192,3 +192,19 @@ def test_multi_gpu_partitioned_run_matches_oracle():
                         "--master-addr", "127.0.0.1", "--master-port", "29517", str(script)],
                        capture_output=True, text=True, timeout=600)
     assert "MULTI_GPU_CHECK PASSED" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("kernel", [0, 1], ids=["row-block-gather", "cell-atomics"])
+def test_assembly_kernel_variants(kernel):
+    c = make_case(nx=40, ny=28, seed=11)
+    o = make_oracle(*c)
+    m = make_model(*c, assembly_kernel=kernel)
+    try:
+        F, J = m.assemble(DT)
+        Fo, Jo = o.assemble(DT)
+        assert relinf(F, Fo) < 1e-12 and relinf(J, Jo) < 1e-12
+        if kernel == 0:                      # no atomics: bitwise reproducible
+            F2, J2 = m.assemble(DT)
+            assert np.array_equal(F, F2) and np.array_equal(J, J2)
+    finally:
+        m.close()
