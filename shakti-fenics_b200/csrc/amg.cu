@@ -1,9 +1,11 @@
 // Smoothed-aggregation AMG (see amg.h).  Symbolic phase on the host (patterns are fixed by
 // the mesh), numeric phase and V-cycle on the device.
 #include "amg.h"
+#include "comm.h"
 
 #include <algorithm>
 #include <cmath>
+#include <map>
 #include <numeric>
 
 namespace shakti {
@@ -61,33 +63,6 @@ static int aggregate(const HostCsr& A, int32_t n, const std::vector<uint8_t>& ex
     ++na;
   }
   return na;
-}
-
-// P pattern: row i -> sorted unique aggregates of the (non-excluded, in-block) neighbours of i
-static HostCsr prolongator_pattern(const HostCsr& A, int32_t n, int32_t na, const std::vector<int32_t>& agg, bool smoothed) {
-  HostCsr P;
-  P.n_rows = n;
-  P.n_cols = na;
-  P.rowptr.assign(n + 1, 0);
-  std::vector<int32_t> tmp;
-  for (int32_t i = 0; i < n; ++i) {
-    tmp.clear();
-    if (agg[i] >= 0) {
-      if (smoothed) {
-        for (int32_t k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k) {
-          const int32_t j = A.col[k];
-          if (j < n && agg[j] >= 0) tmp.push_back(agg[j]);
-        }
-        std::sort(tmp.begin(), tmp.end());
-        tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
-      } else {
-        tmp.push_back(agg[i]);
-      }
-    }
-    P.col.insert(P.col.end(), tmp.begin(), tmp.end());
-    P.rowptr[i + 1] = (int32_t)P.col.size();
-  }
-  return P;
 }
 
 // pattern of A(:, 0:B.n_rows) * B
@@ -341,22 +316,78 @@ amg_gershgorin_kernel(SellView A, const double* __restrict__ dinv, unsigned long
   if ((threadIdx.x & 31) == 0 && v > 0.0) atomicMax(out, (unsigned long long)__double_as_longlong(v));
 }
 
+// ------------------------------------------------------------------ distributed helpers
+// sendbuf[s*w + k] = pos >= 0 ? val[pos] : 0
+__global__ void amg_pack_rows_kernel(int64_t n, const int32_t* __restrict__ pos, const double* __restrict__ val,
+                                     double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t p = pos[i];
+  out[i] = p >= 0 ? val[p] : 0.0;
+}
+// val[pos[i]] = in[i] where pos >= 0
+__global__ void amg_unpack_rows_kernel(int64_t n, const int32_t* __restrict__ pos, const double* __restrict__ in,
+                                       double* __restrict__ val) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t p = pos[i];
+  if (p >= 0) val[p] = in[i];
+}
+// rows of the (distributed) coarsest operator as dense rows in GLOBAL column numbering
+__global__ void amg_dense_rows_kernel(SellView A, const int32_t* __restrict__ Alen, const int32_t* __restrict__ colmap,
+                                      int32_t n, int32_t N, double* __restrict__ D) {
+  const int32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  const int32_t base = A.slice_ptr[row >> 5] + (row & 31);
+  for (int k = 0; k < Alen[row]; ++k) D[(size_t)row * N + colmap[A.col[base + 32 * k]]] += A.val[base + 32 * k];
+}
+// gathered row blocks [rank][nmax][N] -> [A | I] with leading dimension 2N
+__global__ void amg_dense_assemble_kernel(int32_t N, int32_t nmax, int32_t nranks, const int32_t* __restrict__ off,
+                                          const double* __restrict__ G, double* __restrict__ D) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)N * N) return;
+  const int32_t gi = (int32_t)(t / N), j = (int32_t)(t - (int64_t)gi * N);
+  int r = 0;
+  while (r + 1 < nranks && off[r + 1] <= gi) ++r;
+  const int32_t li = gi - off[r];
+  D[(size_t)gi * 2 * N + j] = G[((size_t)r * nmax + li) * N + j];
+  if (j == 0) D[(size_t)gi * 2 * N + N + gi] = 1.0;
+}
+// gathered rhs blocks [rank][nmax] -> global vector
+__global__ void amg_compact_kernel(int32_t N, int32_t nmax, int32_t nranks, const int32_t* __restrict__ off,
+                                   const double* __restrict__ G, double* __restrict__ out) {
+  const int32_t gi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= N) return;
+  int r = 0;
+  while (r + 1 < nranks && off[r + 1] <= gi) ++r;
+  out[gi] = G[(size_t)r * nmax + (gi - off[r])];
+}
+
 // ------------------------------------------------------------------ hierarchy
 struct AmgLevel {
-  int32_t n = 0, n_cols = 0, n_coarse = 0;
+  int32_t n = 0, n_ghost = 0, n_cols = 0;      // owned rows, ghost columns, n + n_ghost
+  int32_t n_coarse = 0, n_coarse_ghost = 0;
   int64_t nnz = 0;
   DevSell A;                  // levels >= 1 (level 0 uses the caller's matrix)
   DevBuf<int32_t> diag_pos;   // levels >= 1
   DevBuf<double> dinv;
-  DevSell P, R, AP;
+  DevSell P, R, AP;           // P: (n + n_ghost) x (n_coarse + n_coarse_ghost); R = (P[owned, owned])^T
   DevBuf<uint8_t> pmap;
   DevBuf<int32_t> tmap;
   DevBuf<double> x, x2, b, r, d, pv;
   bool pv_init = false;       // pv holds the current power-iteration vector (warm start)
   double lmax = 2.0;          // estimate of lambda_max(D^-1 A)
   bool last = false;
-  HostCsr hA;                 // host pattern (levels >= 1), kept for rebuilds of deeper levels
+  HostCsr hA;                 // host pattern (levels >= 1)
   HostSell hS;
+  // halo of this level's vectors (level 0: the caller's plan)
+  std::vector<Neighbor> nbrs;
+  HaloPlan own_halo;
+  HaloPlan* halo = nullptr;
+  // exchange of the prolongator rows of interface vertices
+  int maxw = 0;
+  DevBuf<int32_t> psend_pos, pg_pos;
+  DevBuf<double> psend, precv;
 };
 
 struct Amg::Impl {
@@ -364,9 +395,14 @@ struct Amg::Impl {
   cudaStream_t s = 0;
   const HostCsr* A0 = nullptr;
   const HostSell* S0 = nullptr;
+  const std::vector<Neighbor>* nbrs0 = nullptr;
+  HaloPlan* halo0 = nullptr;
   std::vector<uint8_t> exclude;
   std::vector<std::unique_ptr<AmgLevel>> lv;
-  DevBuf<double> dense;
+  // coarsest level: gathered on every rank and inverted densely
+  DevBuf<double> dense, dense_rows, dense_gather, crhs, cgather, cglob, csol;
+  DevBuf<int32_t> coff, ccolmap;
+  int32_t cN = 0, cnmax = 0, coff_me = 0;
   DevBuf<int> info;
   bool dense_coarse = false;
   bool built = false;
@@ -394,13 +430,15 @@ static std::vector<int32_t> diag_positions(const HostCsr& A, const HostSell& S, 
   return d;
 }
 
-void Amg::setup(const HostCsr& A0, const HostSell& S0, const std::vector<uint8_t>& exclude, const AmgOptions& opt,
-                int sm_count, cudaStream_t s) {
+void Amg::setup(const HostCsr& A0, const HostSell& S0, const std::vector<uint8_t>& exclude, const std::vector<Neighbor>& nbrs,
+                HaloPlan* halo, const AmgOptions& opt, int sm_count, cudaStream_t s) {
   Impl& I = *p_;
   I.opt = opt;
   I.s = s;
   I.A0 = &A0;
   I.S0 = &S0;
+  I.nbrs0 = &nbrs;
+  I.halo0 = halo;
   I.exclude = exclude;
   I.lv.clear();
   I.built = false;
@@ -420,52 +458,67 @@ static void alloc_level_vectors(AmgLevel& L, int level, cudaStream_t s) {
   if (level > 0) L.b.alloc_zero(std::max(L.n, 1), s);
 }
 
-// numeric phase of one level: smoother diagonal, P, R, AP and the next level's operator
+// numeric phase of one level: smoother diagonal, P (own rows, then the neighbours' interface
+// rows by halo exchange), R, AP and the next level's operator
 static void numeric_level(Amg::Impl& I, size_t l, const DevSell& Afine, const int32_t* fine_diag_pos) {
   cudaStream_t s = I.s;
   AmgLevel& L = *I.lv[l];
   const DevSell& A = (l == 0) ? Afine : L.A;
   const int32_t* dpos = (l == 0) ? fine_diag_pos : L.diag_pos.p;
   if (L.n > 0) SHAKTI_LAUNCH(amg_dinv_kernel, div_up(L.n, 256), 256, 0, s, L.n, dpos, A.val.p, L.dinv.p);
-  if (L.last || L.n == 0) return;
+  if (L.last) return;
   SHAKTI_CUDA(cudaMemsetAsync(L.P.val.p, 0, sizeof(double) * L.P.padded, s));
-  SHAKTI_LAUNCH(amg_prolongator_kernel, div_up(L.n, 256), 256, 0, s, view(A), L.pmap.p, dpos, L.dinv.p,
-                I.opt.prolong_omega, L.P.slice_ptr.p, L.P.val.p);
-  SHAKTI_LAUNCH(amg_gather_vals_kernel, (int)std::min<int64_t>(148 * 8, std::max<int64_t>(1, (L.R.padded + 255) / 256)), 256, 0, s,
-                L.R.padded, L.tmap.p, L.P.val.p, L.R.val.p);
+  if (L.n > 0)
+    SHAKTI_LAUNCH(amg_prolongator_kernel, div_up(L.n, 256), 256, 0, s, view(A), L.pmap.p, dpos, L.dinv.p,
+                  I.opt.prolong_omega, L.P.slice_ptr.p, L.P.val.p);
+  if (comm().active() && L.maxw > 0) {
+    const int64_t ns = (int64_t)L.halo->n_send_total() * L.maxw, ng = (int64_t)L.n_ghost * L.maxw;
+    if (ns) SHAKTI_LAUNCH(amg_pack_rows_kernel, div_up(ns, 256), 256, 0, s, ns, L.psend_pos.p, L.P.val.p, L.psend.p);
+    L.halo->exchange_packed(L.psend.p, L.precv.p, L.n, L.maxw, s);
+    if (ng) SHAKTI_LAUNCH(amg_unpack_rows_kernel, div_up(ng, 256), 256, 0, s, ng, L.pg_pos.p, L.precv.p, L.P.val.p);
+  }
+  if (L.R.padded)
+    SHAKTI_LAUNCH(amg_gather_vals_kernel, (int)std::min<int64_t>(148 * 8, std::max<int64_t>(1, (L.R.padded + 255) / 256)), 256, 0, s,
+                  L.R.padded, L.tmap.p, L.P.val.p, L.R.val.p);
   SHAKTI_CUDA(cudaMemsetAsync(L.AP.val.p, 0, sizeof(double) * L.AP.padded, s));
-  SHAKTI_LAUNCH(amg_spgemm_kernel, div_up(L.n, 128), 128, 0, s, view(A), A.rowlen.p, view(L.P), L.P.rowlen.p, L.P.n_rows,
-                L.AP.slice_ptr.p, L.AP.col.p, L.AP.rowlen.p, L.AP.val.p);
+  if (L.n > 0)
+    SHAKTI_LAUNCH(amg_spgemm_kernel, div_up(L.n, 128), 128, 0, s, view(A), A.rowlen.p, view(L.P), L.P.rowlen.p, L.P.n_rows,
+                  L.AP.slice_ptr.p, L.AP.col.p, L.AP.rowlen.p, L.AP.val.p);
   DevSell& Ac = I.lv[l + 1]->A;
   SHAKTI_CUDA(cudaMemsetAsync(Ac.val.p, 0, sizeof(double) * Ac.padded, s));
-  SHAKTI_LAUNCH(amg_spgemm_kernel, div_up(L.R.n_rows, 128), 128, 0, s, view(L.R), L.R.rowlen.p, view(L.AP), L.AP.rowlen.p,
-                L.AP.n_rows, Ac.slice_ptr.p, Ac.col.p, Ac.rowlen.p, Ac.val.p);
+  if (L.R.n_rows > 0)
+    SHAKTI_LAUNCH(amg_spgemm_kernel, div_up(L.R.n_rows, 128), 128, 0, s, view(L.R), L.R.rowlen.p, view(L.AP), L.AP.rowlen.p,
+                  L.AP.n_rows, Ac.slice_ptr.p, Ac.col.p, Ac.rowlen.p, Ac.val.p);
 }
 
 // Upper end of the spectrum of D^-1 A for the Chebyshev smoother, re-estimated at every refresh:
-// min(Gershgorin bound, 1.1 x power-iteration estimate).  The power vector is kept per level, so
-// a few iterations suffice once it is warm.  One host synchronisation per level.
+// min(Gershgorin bound, 1.1 x power-iteration estimate), identical on every rank.
 static double estimate_lmax(Amg::Impl& I, AmgLevel& L, const DevSell& A) {
   cudaStream_t s = I.s;
-  if (L.n == 0) return 1.0;
-  const int grid = div_up(L.n, 256);
-  double* x = L.pv.p;   // n_cols long, entries beyond n stay 0
+  const int grid = div_up(std::max(L.n, 1), 256);
+  double* x = L.pv.p;   // n_cols long
   double* y = L.r.p;
   int iters = 6;
   if (!L.pv_init) {
-    SHAKTI_LAUNCH(amg_hash_fill_kernel, grid, 256, 0, s, L.n, x);
+    if (L.n) SHAKTI_LAUNCH(amg_hash_fill_kernel, grid, 256, 0, s, L.n, x);
     L.pv_init = true;
     iters = 20;
   }
+  auto apply = [&]() {
+    L.halo->exchange(x, s);
+    if (L.n) SHAKTI_LAUNCH(amg_dinv_spmv_kernel, grid, 256, 0, s, view(A), L.dinv.p, x, y);
+    launch_multi_dot(I.red, L.n, 1, y, std::max(L.n, 1), y, I.scal.p, s);
+    comm_allreduce_sum(I.scal.p, 1, s);
+  };
   for (int it = 0; it < iters; ++it) {
-    SHAKTI_LAUNCH(amg_dinv_spmv_kernel, grid, 256, 0, s, view(A), L.dinv.p, x, y);
-    launch_multi_dot(I.red, L.n, 1, y, L.n, y, I.scal.p, s);
-    SHAKTI_LAUNCH(amg_normalize_kernel, grid, 256, 0, s, L.n, y, I.scal.p, x);
+    apply();
+    if (L.n) SHAKTI_LAUNCH(amg_normalize_kernel, grid, 256, 0, s, L.n, y, I.scal.p, x);
   }
-  SHAKTI_LAUNCH(amg_dinv_spmv_kernel, grid, 256, 0, s, view(A), L.dinv.p, x, y);
-  launch_multi_dot(I.red, L.n, 1, y, L.n, y, I.scal.p, s);       // ||D^-1 A x||^2 with ||x|| = 1
+  apply();   // ||D^-1 A x||^2 with ||x|| = 1
   SHAKTI_CUDA(cudaMemsetAsync(I.scal.p + 1, 0, sizeof(double), s));
-  SHAKTI_LAUNCH(amg_gershgorin_kernel, grid, 256, 0, s, view(A), L.dinv.p, reinterpret_cast<unsigned long long*>(I.scal.p + 1));
+  if (L.n)
+    SHAKTI_LAUNCH(amg_gershgorin_kernel, grid, 256, 0, s, view(A), L.dinv.p, reinterpret_cast<unsigned long long*>(I.scal.p + 1));
+  comm_allreduce_max(I.scal.p + 1, 1, s);
   SHAKTI_CUDA(cudaMemcpyAsync(I.host_scal, I.scal.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
   SHAKTI_CUDA(cudaStreamSynchronize(s));
   const double power = std::sqrt(std::max(I.host_scal[0], 0.0));
@@ -484,6 +537,240 @@ static void update_smoother_bounds(Amg::Impl& I, const DevSell& Afine) {
   }
 }
 
+// One coarsening step on the host: rank-local aggregation on strong connections, prolongator
+// pattern over own + ghost aggregates, the neighbours' interface rows of P, R = (P[own,own])^T,
+// the two product patterns and the halo plan of the coarse level.
+static void coarsen_level(Amg::Impl& I, size_t l, const DevSell& dA, const HostCsr& A, const HostSell& S,
+                          const std::vector<uint8_t>& excl, bool& stalled) {
+  cudaStream_t s = I.s;
+  const AmgOptions& opt = I.opt;
+  AmgLevel& L = *I.lv[l];
+  const int me = comm().rank, nranks = comm().nranks;
+  const int32_t n = L.n, g = L.n_ghost;
+  // ---- strength + aggregation (own rows, own columns)
+  std::vector<uint8_t> strong;
+  const double theta = opt.strength_theta * std::pow(0.5, (double)l);
+  if (theta > 0 && n > 0) {
+    std::vector<double> v = dA.val.download(s);
+    std::vector<double> diag(n, 0.0);
+    for (int32_t i = 0; i < n; ++i)
+      for (int32_t k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k)
+        if (A.col[k] == i) diag[i] = std::fabs(v[S.pos(i, k - A.rowptr[i])]);
+    strong.assign(A.nnz(), 0);
+    for (int32_t i = 0; i < n; ++i)
+      for (int32_t k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k) {
+        const int32_t j = A.col[k];
+        if (j >= n || j == i) continue;
+        const double a = std::fabs(v[S.pos(i, k - A.rowptr[i])]);
+        strong[k] = (a >= theta * std::sqrt(diag[i] * diag[j])) && a > 0;
+      }
+  }
+  std::vector<int32_t> agg;
+  const int32_t nc = n > 0 ? aggregate(A, n, excl, strong, agg) : 0;
+  const double nc_glob = comm_host_sum((double)nc, s), n_glob = comm_host_sum((double)n, s);
+  if (nc_glob <= 0 || nc_glob > 0.85 * n_glob) { stalled = true; return; }
+  stalled = false;
+  L.n_coarse = nc;
+  // ---- aggregate of every ghost column: (owner rank, index on the owner) or none
+  std::vector<int> gowner(g, -1);
+  for (const auto& nb : L.nbrs)
+    for (int32_t k = 0; k < nb.recv_count; ++k) gowner[nb.recv_begin - n + k] = nb.rank;
+  std::vector<double> gagg(g, -1.0);
+  if (comm().active()) {
+    std::vector<double> tmp((size_t)n + g, -1.0);
+    for (int32_t i = 0; i < n; ++i) tmp[i] = (double)agg[i];
+    DevBuf<double> dv;
+    dv.upload(tmp);
+    L.halo->exchange(dv.p, s);
+    tmp = dv.download(s);
+    for (int32_t k = 0; k < g; ++k) gagg[k] = tmp[n + k];
+  }
+  typedef std::pair<int, int32_t> Gid;          // (rank, index on that rank)
+  auto gid_of_col = [&](int32_t j) -> Gid {      // aggregate of local column j, (-1,-1) if none
+    if (j < n) return agg[j] >= 0 ? Gid(me, agg[j]) : Gid(-1, -1);
+    const double a = gagg[j - n];
+    return a >= 0 ? Gid(gowner[j - n], (int32_t)a) : Gid(-1, -1);
+  };
+  // ---- prolongator rows of own vertices in global aggregate ids
+  const bool smoothed = opt.prolong_omega != 0.0;
+  std::vector<std::vector<Gid>> prow((size_t)n + g);
+  for (int32_t i = 0; i < n; ++i) {
+    if (agg[i] < 0) continue;
+    auto& r = prow[i];
+    if (smoothed) {
+      for (int32_t k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k) {
+        const Gid c = gid_of_col(A.col[k]);
+        if (c.first >= 0) r.push_back(c);
+      }
+      std::sort(r.begin(), r.end());
+      r.erase(std::unique(r.begin(), r.end()), r.end());
+    } else {
+      r.push_back(Gid(me, agg[i]));
+    }
+  }
+  // ---- interface rows of the neighbours (pattern exchange, fixed width)
+  int maxw = 0;
+  const std::vector<int32_t>& sidx = L.halo->send_idx_host;
+  for (int32_t v : sidx) maxw = std::max<int>(maxw, (int)prow[v].size());
+  maxw = (int)comm_host_max((double)maxw, s);
+  L.maxw = comm().active() ? maxw : 0;
+  if (comm().active() && maxw > 0) {
+    const int wp = 1 + 2 * maxw;
+    std::vector<double> sb((size_t)std::max<size_t>(sidx.size(), 1) * wp, -1.0), rb((size_t)std::max(g, 1) * wp, -1.0);
+    for (size_t k = 0; k < sidx.size(); ++k) {
+      const auto& r = prow[sidx[k]];
+      sb[k * wp] = (double)r.size();
+      for (size_t w = 0; w < r.size(); ++w) { sb[k * wp + 1 + 2 * w] = r[w].first; sb[k * wp + 2 + 2 * w] = r[w].second; }
+    }
+    DevBuf<double> dsb, drb;
+    dsb.upload(sb);
+    drb.upload(rb);
+    L.halo->exchange_packed(dsb.p, drb.p, n, wp, s);
+    rb = drb.download(s);
+    for (int32_t k = 0; k < g; ++k) {
+      const int len = (int)rb[(size_t)k * wp];
+      for (int w = 0; w < len; ++w)
+        prow[(size_t)n + k].push_back(Gid((int)rb[(size_t)k * wp + 1 + 2 * w], (int32_t)rb[(size_t)k * wp + 2 + 2 * w]));
+      // NOTE: kept in the owner's order; slot w of the value exchange refers to this order
+    }
+  }
+  // ---- ghost aggregates: everything referenced that is not mine, sorted by (owner, index)
+  std::vector<Gid> gset;
+  for (const auto& r : prow)
+    for (const Gid& c : r)
+      if (c.first != me) gset.push_back(c);
+  std::sort(gset.begin(), gset.end());
+  gset.erase(std::unique(gset.begin(), gset.end()), gset.end());
+  const int32_t gc = (int32_t)gset.size();
+  L.n_coarse_ghost = gc;
+  auto local_col = [&](const Gid& c) -> int32_t {
+    if (c.first == me) return c.second;
+    return nc + (int32_t)(std::lower_bound(gset.begin(), gset.end(), c) - gset.begin());
+  };
+  // ---- P (n + g rows) with sorted local columns; remember where the exchanged values go
+  HostCsr P;
+  P.n_rows = (int64_t)n + g;
+  P.n_cols = (int64_t)nc + gc;
+  P.rowptr.assign(P.n_rows + 1, 0);
+  std::vector<std::vector<int32_t>> order((size_t)g);   // ghost rows: slot w -> rank in sorted row
+  {
+    std::vector<std::pair<int32_t, int>> tmp;
+    for (int64_t i = 0; i < P.n_rows; ++i) {
+      tmp.clear();
+      for (size_t w = 0; w < prow[i].size(); ++w) tmp.push_back({local_col(prow[i][w]), (int)w});
+      std::sort(tmp.begin(), tmp.end());
+      if (i >= n) order[i - n].assign(tmp.size(), 0);
+      for (size_t q = 0; q < tmp.size(); ++q) {
+        P.col.push_back(tmp[q].first);
+        if (i >= n) order[i - n][tmp[q].second] = (int32_t)q;
+      }
+      P.rowptr[i + 1] = (int32_t)P.col.size();
+    }
+  }
+  HostSell PS = sell_from_csr(P);
+  // pmap: A entry (i,j) -> position of aggregate(j) inside P's row i
+  {
+    std::vector<uint8_t> pm(S.padded(), 255);
+    for (int32_t i = 0; i < n; ++i) {
+      const int32_t* pb = P.col.data() + P.rowptr[i];
+      const int32_t* pe = P.col.data() + P.rowptr[i + 1];
+      if (pb == pe) continue;
+      for (int32_t k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k) {
+        const int32_t j = A.col[k];
+        if (!smoothed && j != i) continue;
+        const Gid c = gid_of_col(j);
+        if (c.first < 0) continue;
+        const int32_t* q = std::lower_bound(pb, pe, local_col(c));
+        const int64_t t = q - pb;
+        if (t > 254) throw Error(SHAKTI_ERR_INVALID, "AMG: prolongator row too long");
+        pm[S.pos(i, k - A.rowptr[i])] = (uint8_t)t;
+      }
+    }
+    L.pmap.upload(pm);
+  }
+  L.P.upload_pattern(PS, P.nnz());
+  if (L.maxw > 0) {
+    // own interface rows: slot w of send entry k = w-th entry of the (sorted-by-Gid) own row; own rows were
+    // built sorted by Gid, and local_col is monotone in Gid only per owner, so map through the sorted order
+    std::vector<int32_t> sp((size_t)std::max<size_t>(sidx.size(), 1) * L.maxw, -1), gp((size_t)std::max(g, 1) * L.maxw, -1);
+    for (size_t k = 0; k < sidx.size(); ++k) {
+      const int32_t i = sidx[k];
+      const int32_t* pb = P.col.data() + P.rowptr[i];
+      const int32_t* pe = P.col.data() + P.rowptr[i + 1];
+      for (size_t w = 0; w < prow[i].size(); ++w) {
+        const int32_t* q = std::lower_bound(pb, pe, local_col(prow[i][w]));
+        sp[k * L.maxw + w] = (int32_t)PS.pos(i, (int)(q - pb));
+      }
+    }
+    for (int32_t k = 0; k < g; ++k)
+      for (size_t w = 0; w < order[k].size(); ++w) gp[(size_t)k * L.maxw + w] = (int32_t)PS.pos((int64_t)n + k, order[k][w]);
+    L.psend_pos.upload(sp);
+    L.pg_pos.upload(gp);
+    L.psend.alloc_zero(sp.size(), s);
+    L.precv.alloc_zero(gp.size(), s);
+  }
+  // ---- R = transpose of the own-rows x own-aggregates block of P
+  HostCsr Pown;
+  Pown.n_rows = n;
+  Pown.n_cols = nc;
+  Pown.rowptr.assign((size_t)n + 1, 0);
+  std::vector<int32_t> pown_entry;   // entry of P for each entry of Pown
+  for (int32_t i = 0; i < n; ++i) {
+    for (int32_t k = P.rowptr[i]; k < P.rowptr[i + 1]; ++k)
+      if (P.col[k] < nc) { Pown.col.push_back(P.col[k]); pown_entry.push_back(k); }
+    Pown.rowptr[i + 1] = (int32_t)Pown.col.size();
+  }
+  std::vector<int32_t> tentry;
+  HostCsr R = csr_transpose(Pown, &tentry);
+  HostSell RS = sell_from_csr(R);
+  {
+    std::vector<int32_t> ppos = sell_positions(P, PS);
+    std::vector<int32_t> tm(RS.padded(), -1);
+    for (int64_t r = 0; r < R.n_rows; ++r)
+      for (int32_t k = R.rowptr[r]; k < R.rowptr[r + 1]; ++k) tm[RS.pos(r, k - R.rowptr[r])] = ppos[pown_entry[tentry[k]]];
+    L.tmap.upload(tm);
+  }
+  L.R.upload_pattern(RS, R.nnz());
+  // ---- product patterns
+  HostCsr AP = product_pattern(A, P);
+  L.AP.upload_pattern(sell_from_csr(AP), AP.nnz());
+  std::unique_ptr<AmgLevel> Ln(new AmgLevel());
+  Ln->hA = product_pattern(R, AP);
+  Ln->hA.n_cols = (int64_t)nc + gc;
+  Ln->hS = sell_from_csr(Ln->hA);
+  Ln->n = nc;
+  Ln->n_ghost = gc;
+  Ln->n_cols = nc + gc;
+  Ln->nnz = Ln->hA.nnz();
+  Ln->A.upload_pattern(Ln->hS, Ln->hA.nnz());
+  Ln->diag_pos.upload(diag_positions(Ln->hA, Ln->hS, nc));
+  // ---- halo plan of the coarse level: ask every owner for the aggregates referenced here
+  if (comm().active()) {
+    std::vector<std::vector<double>> ask(nranks);
+    std::vector<int32_t> rb(nranks, 0), rc(nranks, 0);
+    for (int32_t k = 0; k < gc; ++k) {
+      const int o = gset[k].first;
+      if (rc[o] == 0) rb[o] = nc + k;
+      rc[o]++;
+      ask[o].push_back((double)gset[k].second);
+    }
+    std::vector<std::vector<double>> asked = comm_exchange_lists(ask, s);
+    for (int r = 0; r < nranks; ++r) {
+      if (r == me || (asked[r].empty() && rc[r] == 0)) continue;
+      Neighbor nb;
+      nb.rank = r;
+      for (double v : asked[r]) nb.send_local.push_back((int32_t)v);
+      nb.recv_begin = rb[r];
+      nb.recv_count = rc[r];
+      Ln->nbrs.push_back(std::move(nb));
+    }
+  }
+  Ln->own_halo.build(Ln->nbrs);
+  Ln->halo = &Ln->own_halo;
+  alloc_level_vectors(*Ln, (int)l + 1, s);
+  I.lv.push_back(std::move(Ln));
+}
+
 static void build_hierarchy(Amg::Impl& I, const DevSell& Afine, const int32_t* fine_diag_pos) {
   cudaStream_t s = I.s;
   const AmgOptions& opt = I.opt;
@@ -492,7 +779,10 @@ static void build_hierarchy(Amg::Impl& I, const DevSell& Afine, const int32_t* f
     std::unique_ptr<AmgLevel> L0(new AmgLevel());
     L0->n = (int32_t)I.A0->n_rows;
     L0->n_cols = (int32_t)I.A0->n_cols;
+    L0->n_ghost = L0->n_cols - L0->n;
     L0->nnz = I.A0->nnz();
+    L0->nbrs = *I.nbrs0;
+    L0->halo = I.halo0;
     alloc_level_vectors(*L0, 0, s);
     I.lv.push_back(std::move(L0));
   }
@@ -504,92 +794,60 @@ static void build_hierarchy(Amg::Impl& I, const DevSell& Afine, const int32_t* f
     const HostSell& S = (l == 0) ? *I.S0 : L.hS;
     const DevSell& dA = (l == 0) ? Afine : L.A;
     nnz_sum += (double)A.nnz();
-    const bool stop = (L.n <= opt.coarse_size) || ((int)l + 1 >= opt.max_levels);
-    std::vector<int32_t> agg;
-    int32_t na = 0;
-    if (!stop) {
-      // strength of connection from the current values: |a_ij| >= theta_l sqrt(|a_ii a_jj|)
-      std::vector<uint8_t> strong;
-      const double theta = opt.strength_theta * std::pow(0.5, (double)l);
-      if (theta > 0) {
-        std::vector<double> v = dA.val.download(s);
-        std::vector<double> diag(L.n, 0.0);
-        for (int32_t i = 0; i < L.n; ++i)
-          for (int32_t k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k)
-            if (A.col[k] == i) diag[i] = std::fabs(v[S.pos(i, k - A.rowptr[i])]);
-        strong.assign(A.nnz(), 0);
-        for (int32_t i = 0; i < L.n; ++i)
-          for (int32_t k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k) {
-            const int32_t j = A.col[k];
-            if (j >= L.n || j == i) continue;
-            const double a = std::fabs(v[S.pos(i, k - A.rowptr[i])]);
-            strong[k] = (a >= theta * std::sqrt(diag[i] * diag[j])) && a > 0;
-          }
-      }
-      na = aggregate(A, L.n, excl, strong, agg);
-      if (na <= 0 || na > 0.85 * L.n) na = 0;  // coarsening stalled
-    }
-    if (stop || na == 0) {
+    const double n_glob = comm_host_sum((double)L.n, s);
+    bool stop = (n_glob <= opt.coarse_size) || ((int)l + 1 >= opt.max_levels);
+    bool stalled = false;
+    if (!stop) coarsen_level(I, l, dA, A, S, excl, stalled);
+    if (stop || stalled) {
       L.last = true;
       numeric_level(I, l, Afine, fine_diag_pos);
       break;
     }
-    L.n_coarse = na;
-    HostCsr P = prolongator_pattern(A, L.n, na, agg, opt.prolong_omega != 0.0);
-    HostSell PS = sell_from_csr(P);
-    {
-      std::vector<uint8_t> pm(S.padded(), 255);
-      for (int32_t i = 0; i < L.n; ++i) {
-        const int32_t* pb = P.col.data() + P.rowptr[i];
-        const int32_t* pe = P.col.data() + P.rowptr[i + 1];
-        if (pb == pe) continue;
-        for (int32_t k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k) {
-          const int32_t j = A.col[k];
-          if (j >= L.n || agg[j] < 0) continue;
-          if (opt.prolong_omega == 0.0 && j != i) continue;
-          const int32_t* q = std::lower_bound(pb, pe, agg[j]);
-          const int64_t t = q - pb;
-          if (t > 254) throw Error(SHAKTI_ERR_INVALID, "AMG: prolongator row too long");
-          pm[S.pos(i, k - A.rowptr[i])] = (uint8_t)t;
-        }
-      }
-      L.pmap.upload(pm);
-    }
-    L.P.upload_pattern(PS, P.nnz());
-    std::vector<int32_t> tentry;
-    HostCsr R = csr_transpose(P, &tentry);
-    HostSell RS = sell_from_csr(R);
-    {
-      std::vector<int32_t> ppos = sell_positions(P, PS);
-      std::vector<int32_t> tm(RS.padded(), -1);
-      for (int64_t r = 0; r < R.n_rows; ++r)
-        for (int32_t k = R.rowptr[r]; k < R.rowptr[r + 1]; ++k) tm[RS.pos(r, k - R.rowptr[r])] = ppos[tentry[k]];
-      L.tmap.upload(tm);
-    }
-    L.R.upload_pattern(RS, R.nnz());
-    HostCsr AP = product_pattern(A, P);
-    L.AP.upload_pattern(sell_from_csr(AP), AP.nnz());
-    std::unique_ptr<AmgLevel> Ln(new AmgLevel());
-    Ln->hA = product_pattern(R, AP);
-    Ln->hA.n_cols = na;
-    Ln->hS = sell_from_csr(Ln->hA);
-    Ln->n = na;
-    Ln->n_cols = na;
-    Ln->nnz = Ln->hA.nnz();
-    Ln->A.upload_pattern(Ln->hS, Ln->hA.nnz());
-    Ln->diag_pos.upload(diag_positions(Ln->hA, Ln->hS, na));
-    alloc_level_vectors(*Ln, (int)l + 1, s);
-    I.lv.push_back(std::move(Ln));
     numeric_level(I, l, Afine, fine_diag_pos);
     excl.clear();
   }
+  // ---- coarsest level: gather on every rank, invert densely
   AmgLevel& last = *I.lv.back();
-  I.dense_coarse = last.n <= 512;
+  const std::vector<double> counts = comm_host_allgather((double)last.n, s);
+  int64_t N = 0, nmax = 0;
+  std::vector<int32_t> off(counts.size() + 1, 0);
+  for (size_t r = 0; r < counts.size(); ++r) {
+    off[r + 1] = off[r] + (int32_t)counts[r];
+    nmax = std::max<int64_t>(nmax, (int64_t)counts[r]);
+  }
+  N = off.back();
+  I.dense_coarse = N <= 1024 && N > 0;
   if (I.dense_coarse) {
-    I.dense.alloc_zero(std::max<size_t>(1, (size_t)2 * last.n * last.n), s);
+    const int me = comm().rank, nr = comm().nranks;
+    I.cN = (int32_t)N;
+    I.cnmax = (int32_t)nmax;
+    I.coff_me = off[me];
+    I.coff.upload(off);
+    std::vector<int32_t> colmap(std::max(last.n_cols, 1), 0);
+    for (int32_t c = 0; c < last.n; ++c) colmap[c] = off[me] + c;
+    if (last.n_ghost > 0) {
+      // ghost column -> (owner, index on owner): recorded when the level was created (its nbrs lists give the owner,
+      // the index is recovered by asking the owners, exactly as for the halo plan)
+      std::vector<double> tmp((size_t)last.n_cols, 0.0);
+      for (int32_t c = 0; c < last.n; ++c) tmp[c] = (double)(off[me] + c);
+      DevBuf<double> dv;
+      dv.upload(tmp);
+      last.halo->exchange(dv.p, s);
+      tmp = dv.download(s);
+      for (int32_t c = last.n; c < last.n_cols; ++c) colmap[c] = (int32_t)tmp[c];
+    }
+    I.ccolmap.upload(colmap);
+    I.dense.alloc_zero((size_t)2 * N * N, s);
+    I.dense_rows.alloc_zero((size_t)std::max<int64_t>(nmax, 1) * N, s);
+    I.dense_gather.alloc_zero((size_t)nr * std::max<int64_t>(nmax, 1) * N, s);
+    I.crhs.alloc_zero(std::max<int64_t>(nmax, 1), s);
+    I.cgather.alloc_zero((size_t)nr * std::max<int64_t>(nmax, 1), s);
+    I.cglob.alloc_zero(N, s);
+    I.csol.alloc_zero(N, s);
     I.info.alloc_zero(1, s);
   }
-  const double nnz0 = (double)I.A0->nnz();
+  const double nnz0 = comm_host_sum((double)I.A0->nnz(), s);
+  nnz_sum = comm_host_sum(nnz_sum, s);
   I.op_complexity = nnz0 > 0 ? nnz_sum / nnz0 : 0.0;
   I.built = true;
 }
@@ -602,12 +860,13 @@ void Amg::refresh_fine_smoother(const DevSell& Afine, const int32_t* fine_diag_p
   cudaStream_t s = I.s;
   if (!I.built || I.lv.empty()) return;
   AmgLevel& L = *I.lv[0];
-  if (L.n == 0) return;
-  SHAKTI_LAUNCH(amg_dinv_kernel, div_up(L.n, 256), 256, 0, s, L.n, fine_diag_pos, Afine.val.p, L.dinv.p);
+  if (L.n > 0) SHAKTI_LAUNCH(amg_dinv_kernel, div_up(L.n, 256), 256, 0, s, L.n, fine_diag_pos, Afine.val.p, L.dinv.p);
   if (I.opt.smoother != 1 || (L.last && I.dense_coarse)) return;
   SHAKTI_CUDA(cudaMemsetAsync(I.scal.p + 1, 0, sizeof(double), s));
-  SHAKTI_LAUNCH(amg_gershgorin_kernel, div_up(L.n, 256), 256, 0, s, view(Afine), L.dinv.p,
-                reinterpret_cast<unsigned long long*>(I.scal.p + 1));
+  if (L.n > 0)
+    SHAKTI_LAUNCH(amg_gershgorin_kernel, div_up(L.n, 256), 256, 0, s, view(Afine), L.dinv.p,
+                  reinterpret_cast<unsigned long long*>(I.scal.p + 1));
+  comm_allreduce_max(I.scal.p + 1, 1, s);
   SHAKTI_CUDA(cudaMemcpyAsync(I.host_scal, I.scal.p + 1, sizeof(double), cudaMemcpyDeviceToHost, s));
   SHAKTI_CUDA(cudaStreamSynchronize(s));
   if (I.host_scal[0] > 0 && std::isfinite(I.host_scal[0])) L.lmax = I.host_scal[0];
@@ -623,23 +882,26 @@ void Amg::refresh(const DevSell& Afine, const int32_t* fine_diag_pos) {
   if (I.dense_coarse) {
     AmgLevel& L = *I.lv.back();
     const DevSell& A = (I.lv.size() == 1) ? Afine : L.A;
-    const int n = L.n;
-    if (n > 0) {
-      SHAKTI_CUDA(cudaMemsetAsync(I.dense.p, 0, sizeof(double) * 2 * (size_t)n * n, s));
-      SHAKTI_CUDA(cudaMemsetAsync(I.info.p, 0, sizeof(int), s));
-      SHAKTI_LAUNCH(amg_dense_fill_kernel, div_up(n, 128), 128, 0, s, view(A), A.rowlen.p, n, I.dense.p);
-      SHAKTI_LAUNCH(amg_dense_invert_kernel, 1, 1024, n * sizeof(double), s, n, I.dense.p, I.info.p);
-    }
+    const int32_t N = I.cN, nmax = std::max(I.cnmax, 1);
+    SHAKTI_CUDA(cudaMemsetAsync(I.dense_rows.p, 0, sizeof(double) * (size_t)nmax * N, s));
+    if (L.n > 0)
+      SHAKTI_LAUNCH(amg_dense_rows_kernel, div_up(L.n, 128), 128, 0, s, view(A), A.rowlen.p, I.ccolmap.p, L.n, N, I.dense_rows.p);
+    comm_allgather(I.dense_rows.p, I.dense_gather.p, nmax * N, s);
+    SHAKTI_CUDA(cudaMemsetAsync(I.dense.p, 0, sizeof(double) * 2 * (size_t)N * N, s));
+    SHAKTI_CUDA(cudaMemsetAsync(I.info.p, 0, sizeof(int), s));
+    SHAKTI_LAUNCH(amg_dense_assemble_kernel, div_up((int64_t)N * N, 256), 256, 0, s, N, nmax, comm().nranks, I.coff.p,
+                  I.dense_gather.p, I.dense.p);
+    SHAKTI_LAUNCH(amg_dense_invert_kernel, 1, 1024, N * sizeof(double), s, N, I.dense.p, I.info.p);
   }
   ++refreshes_;
 }
 
 // `sweeps` smoothing steps on A x = b, in place on L.x (ping-pong with L.x2).  zero_guess: L.x is
-// taken as 0 and the first step needs no SpMV.
+// taken as 0 and the first step needs no SpMV.  Every SpMV is preceded by the level's halo exchange.
 static void smooth(Amg::Impl& I, AmgLevel& L, const DevSell& A, const double* b, int sweeps, bool zero_guess) {
   cudaStream_t s = I.s;
   if (sweeps <= 0) {
-    if (zero_guess) launch_fill(L.n, 0.0, L.x.p, s);
+    if (zero_guess && L.n) launch_fill(L.n, 0.0, L.x.p, s);
     return;
   }
   if (I.opt.smoother == 1) {   // Chebyshev polynomial of degree `sweeps` on D^-1 A, interval [lmax/ratio, lmax]
@@ -648,7 +910,7 @@ static void smooth(Amg::Impl& I, AmgLevel& L, const DevSell& A, const double* b,
     double rho = 1.0 / sigma;
     int k0 = 0;
     if (zero_guess) {
-      SHAKTI_LAUNCH(amg_cheby_first_kernel, div_up(L.n, 256), 256, 0, s, L.n, L.dinv.p, b, 1.0 / theta, L.d.p, L.x.p);
+      if (L.n) SHAKTI_LAUNCH(amg_cheby_first_kernel, div_up(L.n, 256), 256, 0, s, L.n, L.dinv.p, b, 1.0 / theta, L.d.p, L.x.p);
       k0 = 1;
     }
     for (int k = k0; k < sweeps; ++k) {
@@ -660,15 +922,18 @@ static void smooth(Amg::Impl& I, AmgLevel& L, const DevSell& A, const double* b,
         c2 = 2.0 * rho_n / delta;
         rho = rho_n;
       }
-      SHAKTI_LAUNCH(amg_cheby_kernel, div_up((int64_t)A.n_slices * 32, 256), 256, 0, s, view(A), L.dinv.p, b, L.x.p, L.d.p,
-                    L.x2.p, c1, c2);
+      L.halo->exchange(L.x.p, s);
+      if (L.n)
+        SHAKTI_LAUNCH(amg_cheby_kernel, div_up((int64_t)A.n_slices * 32, 256), 256, 0, s, view(A), L.dinv.p, b, L.x.p, L.d.p,
+                      L.x2.p, c1, c2);
       std::swap(L.x.p, L.x2.p);
     }
   } else {                      // damped Jacobi
     const double om = I.opt.smoother_omega;
     int k0 = 0;
-    if (zero_guess) { launch_pointwise_mul(L.n, L.dinv.p, b, om, L.x.p, s); k0 = 1; }
+    if (zero_guess) { if (L.n) launch_pointwise_mul(L.n, L.dinv.p, b, om, L.x.p, s); k0 = 1; }
     for (int k = k0; k < sweeps; ++k) {
+      L.halo->exchange(L.x.p, s);
       launch_jacobi(view(A), L.dinv.p, b, L.x.p, L.x2.p, om, s);
       std::swap(L.x.p, L.x2.p);
     }
@@ -683,13 +948,26 @@ void Amg::apply(const DevSell& Afine, const double* rin, double* z) {
     AmgLevel& L = *I.lv[l];
     const DevSell& A = (l == 0) ? Afine : L.A;
     const double* b = (l == 0) ? rin : L.b.p;
-    if (L.n == 0) continue;
     if (L.last) {
-      if (I.dense_coarse) SHAKTI_LAUNCH(amg_dense_apply_kernel, div_up((int64_t)L.n * 32, 128), 128, 0, s, L.n, I.dense.p, b, L.x.p);
-      else smooth(I, L, A, b, 8, true);
+      if (I.dense_coarse) {
+        const int32_t N = I.cN, nmax = std::max(I.cnmax, 1);
+        if (comm().active()) {
+          SHAKTI_CUDA(cudaMemsetAsync(I.crhs.p, 0, sizeof(double) * nmax, s));
+          if (L.n) SHAKTI_CUDA(cudaMemcpyAsync(I.crhs.p, b, sizeof(double) * L.n, cudaMemcpyDeviceToDevice, s));
+          comm_allgather(I.crhs.p, I.cgather.p, nmax, s);
+          SHAKTI_LAUNCH(amg_compact_kernel, div_up(N, 128), 128, 0, s, N, nmax, comm().nranks, I.coff.p, I.cgather.p, I.cglob.p);
+          SHAKTI_LAUNCH(amg_dense_apply_kernel, div_up((int64_t)N * 32, 128), 128, 0, s, N, I.dense.p, I.cglob.p, I.csol.p);
+          if (L.n) SHAKTI_CUDA(cudaMemcpyAsync(L.x.p, I.csol.p + I.coff_me, sizeof(double) * L.n, cudaMemcpyDeviceToDevice, s));
+        } else if (L.n) {
+          SHAKTI_LAUNCH(amg_dense_apply_kernel, div_up((int64_t)L.n * 32, 128), 128, 0, s, L.n, I.dense.p, b, L.x.p);
+        }
+      } else {
+        smooth(I, L, A, b, 8, true);
+      }
       break;
     }
     smooth(I, L, A, b, I.opt.presmooth, true);
+    L.halo->exchange(L.x.p, s);
     launch_residual(view(A), L.x.p, b, L.r.p, s);
     launch_spmv(view(L.R), L.r.p, I.lv[l + 1]->b.p, s);
   }
@@ -697,8 +975,10 @@ void Amg::apply(const DevSell& Afine, const double* rin, double* z) {
     AmgLevel& L = *I.lv[l];
     const DevSell& A = (l == 0) ? Afine : L.A;
     const double* b = (l == 0) ? rin : L.b.p;
-    if (L.n == 0) continue;
-    launch_spmv_add(view(L.P), I.lv[l + 1]->x.p, L.x.p, s);
+    AmgLevel& C = *I.lv[l + 1];
+    C.halo->exchange(C.x.p, s);
+    // own rows and ghost rows of P: the ghost part of x comes out consistent with its owner
+    launch_spmv_add(view(L.P), C.x.p, L.x.p, s);
     smooth(I, L, A, b, I.opt.postsmooth, false);
   }
   AmgLevel& L0 = *I.lv[0];

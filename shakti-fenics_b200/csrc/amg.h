@@ -31,8 +31,12 @@ class Amg {
   // coarsened; A and S must outlive this object).  `exclude[i] != 0` rows (Dirichlet) stay out
   // of the coarse space.  The hierarchy itself is built by the first refresh(), level by level:
   // strength of connection needs the values, so host symbolic work and device numerics interleave.
-  void setup(const HostCsr& A, const HostSell& S, const std::vector<uint8_t>& exclude, const AmgOptions& opt,
-             int sm_count, cudaStream_t s);
+  // `nbrs`/`halo`: halo description and plan of the fine level (empty / unused on one GPU).  On
+  // several GPUs the hierarchy is global: aggregates stay inside a rank, P reaches the neighbours'
+  // aggregates, R = (P[own rows, own aggregates])^T, every level has its own halo plan, and the
+  // coarsest operator is gathered on all ranks.
+  void setup(const HostCsr& A, const HostSell& S, const std::vector<uint8_t>& exclude, const std::vector<Neighbor>& nbrs,
+             struct HaloPlan* halo, const AmgOptions& opt, int sm_count, cudaStream_t s);
   // Numeric phase: recompute P, R, coarse operators and smoother diagonals from the fine values.
   void refresh(const DevSell& Afine, const int32_t* fine_diag_pos);
   // Per-solve update of the fine-level smoother only (diagonal + safe Chebyshev bound) for

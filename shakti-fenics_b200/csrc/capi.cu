@@ -212,7 +212,7 @@ static void ensure_amg(shakti_model* m) {
   std::vector<uint8_t> excl = m->isbc.download(m->stream);
   excl.resize(m->hm.n_owned);
   m->amg.reset(new Amg());
-  m->amg->setup(m->hm.A, m->hm.S, excl, ao, m->sm_count, m->stream);
+  m->amg->setup(m->hm.A, m->hm.S, excl, m->hm.nbrs, &m->halo, ao, m->sm_count, m->stream);
   m->amg_setup_done = true;
   m->solves_since_refresh = 0;
 }
