@@ -228,16 +228,17 @@ amg_dense_invert_kernel(int32_t n, double* __restrict__ D, int* __restrict__ inf
 }
 
 // x = Ainv b, Ainv = right half of D; one warp per row
-__global__ void amg_dense_apply_kernel(int32_t n, const double* __restrict__ D, const double* __restrict__ b,
-                                       double* __restrict__ x) {
+template <class TB, class TX>
+__global__ void amg_dense_apply_kernel(int32_t n, const double* __restrict__ D, const TB* __restrict__ b,
+                                       TX* __restrict__ x) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= n) return;
   const double* row = D + (size_t)warp * 2 * n + n;
   double acc = 0.0;
-  for (int j = lane; j < n; j += 32) acc += row[j] * b[j];
+  for (int j = lane; j < n; j += 32) acc += row[j] * (double)b[j];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0) x[warp] = acc;
+  if (lane == 0) x[warp] = (TX)acc;
 }
 
 // ------------------------------------------------------------------ smoother kernels
@@ -261,31 +262,33 @@ amg_dinv_spmv_kernel(SellView A, const double* __restrict__ dinv, const double* 
   y[row] = dinv[row] * acc;
 }
 // Chebyshev step: r = dinv (b - A x); d = c1 d + c2 r; x_out = x + d
+template <class T>
 __global__ void __launch_bounds__(256)
-amg_cheby_kernel(SellView A, const double* __restrict__ dinv, const double* __restrict__ b, const double* __restrict__ x,
-                 double* __restrict__ d, double* __restrict__ x_out, double c1, double c2) {
+amg_cheby_kernel(SellViewT<T> A, const T* __restrict__ dinv, const T* __restrict__ b, const T* __restrict__ x,
+                 T* __restrict__ d, T* __restrict__ x_out, T c1, T c2) {
   const int32_t row = blockIdx.x * blockDim.x + threadIdx.x;
   const int32_t slice = row >> 5;
   if (slice >= A.n_slices) return;
   const int32_t base = A.slice_ptr[slice];
   const int32_t w = (A.slice_ptr[slice + 1] - base) >> 5;
   const int32_t* __restrict__ cp = A.col + base + (row & 31);
-  const double* __restrict__ vp = A.val + base + (row & 31);
-  double acc = 0.0;
+  const T* __restrict__ vp = A.val + base + (row & 31);
+  T acc = 0;
 #pragma unroll 4
   for (int k = 0; k < w; ++k) acc += vp[32 * k] * x[cp[32 * k]];
   if (row >= A.n_rows) return;
-  const double r = dinv[row] * (b[row] - acc);
-  const double dn = c1 * d[row] + c2 * r;
+  const T r = dinv[row] * (b[row] - acc);
+  const T dn = c1 * d[row] + c2 * r;
   d[row] = dn;
   x_out[row] = x[row] + dn;
 }
 // first Chebyshev step from a zero guess: d = (dinv b)/theta ; x = d
-__global__ void amg_cheby_first_kernel(int32_t n, const double* __restrict__ dinv, const double* __restrict__ b,
-                                       double inv_theta, double* __restrict__ d, double* __restrict__ x) {
+template <class T>
+__global__ void amg_cheby_first_kernel(int32_t n, const T* __restrict__ dinv, const T* __restrict__ b, T inv_theta,
+                                       T* __restrict__ d, T* __restrict__ x) {
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const double v = dinv[i] * b[i] * inv_theta;
+  const T v = dinv[i] * b[i] * inv_theta;
   d[i] = v;
   x[i] = v;
 }
@@ -363,7 +366,18 @@ __global__ void amg_compact_kernel(int32_t N, int32_t nmax, int32_t nranks, cons
   out[gi] = G[(size_t)r * nmax + (gi - off[r])];
 }
 
+template <class TI, class TO>
+__global__ void amg_convert_kernel(int32_t n, const TI* __restrict__ in, TO* __restrict__ out) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (TO)in[i];
+}
+
 // ------------------------------------------------------------------ hierarchy
+template <class T>
+struct CycleVecs {
+  DevBuf<T> x, x2, b, r, d, dinv;
+};
+
 struct AmgLevel {
   int32_t n = 0, n_ghost = 0, n_cols = 0;      // owned rows, ghost columns, n + n_ghost
   int32_t n_coarse = 0, n_coarse_ghost = 0;
@@ -374,7 +388,9 @@ struct AmgLevel {
   DevSell P, R, AP;           // P: (n + n_ghost) x (n_coarse + n_coarse_ghost); R = (P[owned, owned])^T
   DevBuf<uint8_t> pmap;
   DevBuf<int32_t> tmap;
-  DevBuf<double> x, x2, b, r, d, pv;
+  DevBuf<double> r, pv;       // double scratch of the spectrum estimate
+  CycleVecs<double> vd;       // V-cycle work vectors, double ...
+  CycleVecs<float> vf;        // ... or single precision (mixed-precision cycle)
   bool pv_init = false;       // pv holds the current power-iteration vector (warm start)
   double lmax = 2.0;          // estimate of lambda_max(D^-1 A)
   bool last = false;
@@ -448,15 +464,25 @@ void Amg::setup(const HostCsr& A0, const HostSell& S0, const std::vector<uint8_t
   refreshes_ = 0;
 }
 
-static void alloc_level_vectors(AmgLevel& L, int level, cudaStream_t s) {
-  L.dinv.alloc_zero(std::max(L.n, 1), s);
-  L.x.alloc_zero(std::max(L.n_cols, 1), s);
-  L.x2.alloc_zero(std::max(L.n_cols, 1), s);
-  L.r.alloc_zero(std::max(L.n, 1), s);
-  L.d.alloc_zero(std::max(L.n, 1), s);
-  L.pv.alloc_zero(std::max(L.n_cols, 1), s);
-  if (level > 0) L.b.alloc_zero(std::max(L.n, 1), s);
+template <class T>
+static void alloc_cycle_vectors(CycleVecs<T>& v, const AmgLevel& L, cudaStream_t s) {
+  v.x.alloc_zero(std::max(L.n_cols, 1), s);
+  v.x2.alloc_zero(std::max(L.n_cols, 1), s);
+  v.b.alloc_zero(std::max(L.n, 1), s);
+  v.r.alloc_zero(std::max(L.n, 1), s);
+  v.d.alloc_zero(std::max(L.n, 1), s);
+  v.dinv.alloc_zero(std::max(L.n, 1), s);
 }
+static void alloc_level_vectors(AmgLevel& L, bool fp32, cudaStream_t s) {
+  L.dinv.alloc_zero(std::max(L.n, 1), s);
+  L.r.alloc_zero(std::max(L.n, 1), s);
+  L.pv.alloc_zero(std::max(L.n_cols, 1), s);
+  if (fp32) alloc_cycle_vectors(L.vf, L, s);
+  else alloc_cycle_vectors(L.vd, L, s);
+}
+template <class T> static CycleVecs<T>& vecs(AmgLevel& L);
+template <> CycleVecs<double>& vecs<double>(AmgLevel& L) { return L.vd; }
+template <> CycleVecs<float>& vecs<float>(AmgLevel& L) { return L.vf; }
 
 // numeric phase of one level: smoother diagonal, P (own rows, then the neighbours' interface
 // rows by halo exchange), R, AP and the next level's operator
@@ -489,6 +515,21 @@ static void numeric_level(Amg::Impl& I, size_t l, const DevSell& Afine, const in
   if (L.R.n_rows > 0)
     SHAKTI_LAUNCH(amg_spgemm_kernel, div_up(L.R.n_rows, 128), 128, 0, s, view(L.R), L.R.rowlen.p, view(L.AP), L.AP.rowlen.p,
                   L.AP.n_rows, Ac.slice_ptr.p, Ac.col.p, Ac.rowlen.p, Ac.val.p);
+}
+
+// Copies the V-cycle reads: smoother diagonal in the cycle's precision and, for the mixed-precision
+// cycle, single-precision values of A, P and R.
+static void sync_cycle_precision(Amg::Impl& I, size_t l, const DevSell& Afine, bool matrices) {
+  cudaStream_t s = I.s;
+  AmgLevel& L = *I.lv[l];
+  const DevSell& A = (l == 0) ? Afine : L.A;
+  if (I.opt.fp32_cycle) {
+    launch_d2f(L.n, L.dinv.p, L.vf.dinv.p, s);
+    A.refresh_f32(s);
+    if (matrices && !L.last) { L.P.refresh_f32(s); L.R.refresh_f32(s); }
+  } else if (L.n) {
+    SHAKTI_CUDA(cudaMemcpyAsync(L.vd.dinv.p, L.dinv.p, sizeof(double) * L.n, cudaMemcpyDeviceToDevice, s));
+  }
 }
 
 // Upper end of the spectrum of D^-1 A for the Chebyshev smoother, re-estimated at every refresh:
@@ -767,7 +808,7 @@ static void coarsen_level(Amg::Impl& I, size_t l, const DevSell& dA, const HostC
   }
   Ln->own_halo.build(Ln->nbrs);
   Ln->halo = &Ln->own_halo;
-  alloc_level_vectors(*Ln, (int)l + 1, s);
+  alloc_level_vectors(*Ln, I.opt.fp32_cycle != 0, s);
   I.lv.push_back(std::move(Ln));
 }
 
@@ -783,7 +824,7 @@ static void build_hierarchy(Amg::Impl& I, const DevSell& Afine, const int32_t* f
     L0->nnz = I.A0->nnz();
     L0->nbrs = *I.nbrs0;
     L0->halo = I.halo0;
-    alloc_level_vectors(*L0, 0, s);
+    alloc_level_vectors(*L0, I.opt.fp32_cycle != 0, s);
     I.lv.push_back(std::move(L0));
   }
   std::vector<uint8_t> excl = I.exclude;
@@ -861,7 +902,7 @@ void Amg::refresh_fine_smoother(const DevSell& Afine, const int32_t* fine_diag_p
   if (!I.built || I.lv.empty()) return;
   AmgLevel& L = *I.lv[0];
   if (L.n > 0) SHAKTI_LAUNCH(amg_dinv_kernel, div_up(L.n, 256), 256, 0, s, L.n, fine_diag_pos, Afine.val.p, L.dinv.p);
-  if (I.opt.smoother != 1 || (L.last && I.dense_coarse)) return;
+  if (I.opt.smoother != 1 || (L.last && I.dense_coarse)) { sync_cycle_precision(I, 0, Afine, false); return; }
   SHAKTI_CUDA(cudaMemsetAsync(I.scal.p + 1, 0, sizeof(double), s));
   if (L.n > 0)
     SHAKTI_LAUNCH(amg_gershgorin_kernel, div_up(L.n, 256), 256, 0, s, view(Afine), L.dinv.p,
@@ -870,6 +911,7 @@ void Amg::refresh_fine_smoother(const DevSell& Afine, const int32_t* fine_diag_p
   SHAKTI_CUDA(cudaMemcpyAsync(I.host_scal, I.scal.p + 1, sizeof(double), cudaMemcpyDeviceToHost, s));
   SHAKTI_CUDA(cudaStreamSynchronize(s));
   if (I.host_scal[0] > 0 && std::isfinite(I.host_scal[0])) L.lmax = I.host_scal[0];
+  sync_cycle_precision(I, 0, Afine, false);
 }
 
 void Amg::refresh(const DevSell& Afine, const int32_t* fine_diag_pos) {
@@ -879,6 +921,7 @@ void Amg::refresh(const DevSell& Afine, const int32_t* fine_diag_pos) {
   else
     for (size_t l = 0; l < I.lv.size(); ++l) numeric_level(I, l, Afine, fine_diag_pos);
   update_smoother_bounds(I, Afine);
+  for (size_t l = 0; l < I.lv.size(); ++l) sync_cycle_precision(I, l, Afine, true);
   if (I.dense_coarse) {
     AmgLevel& L = *I.lv.back();
     const DevSell& A = (I.lv.size() == 1) ? Afine : L.A;
@@ -896,12 +939,15 @@ void Amg::refresh(const DevSell& Afine, const int32_t* fine_diag_pos) {
   ++refreshes_;
 }
 
-// `sweeps` smoothing steps on A x = b, in place on L.x (ping-pong with L.x2).  zero_guess: L.x is
-// taken as 0 and the first step needs no SpMV.  Every SpMV is preceded by the level's halo exchange.
-static void smooth(Amg::Impl& I, AmgLevel& L, const DevSell& A, const double* b, int sweeps, bool zero_guess) {
+// `sweeps` smoothing steps on A x = b, in place on v.x (ping-pong with v.x2).  zero_guess: v.x is
+// taken as 0 and the first step needs no SpMV.  Every SpMV is preceded by the level's halo exchange
+// unless the caller says the ghosts are already current.
+template <class T>
+static void smooth(Amg::Impl& I, AmgLevel& L, const DevSell& A, const T* b, int sweeps, bool zero_guess, bool ghosts_current) {
   cudaStream_t s = I.s;
+  CycleVecs<T>& v = vecs<T>(L);
   if (sweeps <= 0) {
-    if (zero_guess && L.n) launch_fill(L.n, 0.0, L.x.p, s);
+    if (zero_guess) launch_fill_t<T>(L.n, (T)0, v.x.p, s);
     return;
   }
   if (I.opt.smoother == 1) {   // Chebyshev polynomial of degree `sweeps` on D^-1 A, interval [lmax/ratio, lmax]
@@ -910,7 +956,7 @@ static void smooth(Amg::Impl& I, AmgLevel& L, const DevSell& A, const double* b,
     double rho = 1.0 / sigma;
     int k0 = 0;
     if (zero_guess) {
-      if (L.n) SHAKTI_LAUNCH(amg_cheby_first_kernel, div_up(L.n, 256), 256, 0, s, L.n, L.dinv.p, b, 1.0 / theta, L.d.p, L.x.p);
+      if (L.n) SHAKTI_LAUNCH((amg_cheby_first_kernel<T>), div_up(L.n, 256), 256, 0, s, L.n, v.dinv.p, b, (T)(1.0 / theta), v.d.p, v.x.p);
       k0 = 1;
     }
     for (int k = k0; k < sweeps; ++k) {
@@ -922,67 +968,81 @@ static void smooth(Amg::Impl& I, AmgLevel& L, const DevSell& A, const double* b,
         c2 = 2.0 * rho_n / delta;
         rho = rho_n;
       }
-      L.halo->exchange(L.x.p, s);
+      if (!(ghosts_current && k == k0)) L.halo->exchange(v.x.p, s);
       if (L.n)
-        SHAKTI_LAUNCH(amg_cheby_kernel, div_up((int64_t)A.n_slices * 32, 256), 256, 0, s, view(A), L.dinv.p, b, L.x.p, L.d.p,
-                      L.x2.p, c1, c2);
-      std::swap(L.x.p, L.x2.p);
+        SHAKTI_LAUNCH((amg_cheby_kernel<T>), div_up((int64_t)A.n_slices * 32, 256), 256, 0, s, view_as<T>(A), v.dinv.p, b, v.x.p,
+                      v.d.p, v.x2.p, (T)c1, (T)c2);
+      std::swap(v.x.p, v.x2.p);
     }
   } else {                      // damped Jacobi
     const double om = I.opt.smoother_omega;
     int k0 = 0;
-    if (zero_guess) { if (L.n) launch_pointwise_mul(L.n, L.dinv.p, b, om, L.x.p, s); k0 = 1; }
+    if (zero_guess) { launch_scaled_mul<T>(L.n, v.dinv.p, b, om, v.x.p, s); k0 = 1; }
     for (int k = k0; k < sweeps; ++k) {
-      L.halo->exchange(L.x.p, s);
-      launch_jacobi(view(A), L.dinv.p, b, L.x.p, L.x2.p, om, s);
-      std::swap(L.x.p, L.x2.p);
+      if (!(ghosts_current && k == k0)) L.halo->exchange(v.x.p, s);
+      launch_jacobi<T>(view_as<T>(A), v.dinv.p, b, v.x.p, v.x2.p, om, s);
+      std::swap(v.x.p, v.x2.p);
     }
+  }
+}
+
+template <class T>
+static void vcycle(Amg::Impl& I, const DevSell& Afine) {
+  cudaStream_t s = I.s;
+  const int nl = (int)I.lv.size();
+  for (int l = 0; l < nl; ++l) {   // downward; level l's right-hand side is vecs(l).b
+    AmgLevel& L = *I.lv[l];
+    CycleVecs<T>& v = vecs<T>(L);
+    const DevSell& A = (l == 0) ? Afine : L.A;
+    if (L.last) {
+      if (I.dense_coarse) {
+        const int32_t N = I.cN, nmax = std::max(I.cnmax, 1);
+        if (comm().active()) {
+          SHAKTI_CUDA(cudaMemsetAsync(I.crhs.p, 0, sizeof(double) * nmax, s));
+          if (L.n) SHAKTI_LAUNCH((amg_convert_kernel<T, double>), div_up(L.n, 256), 256, 0, s, L.n, v.b.p, I.crhs.p);
+          comm_allgather(I.crhs.p, I.cgather.p, nmax, s);
+          SHAKTI_LAUNCH(amg_compact_kernel, div_up(N, 128), 128, 0, s, N, nmax, comm().nranks, I.coff.p, I.cgather.p, I.cglob.p);
+          SHAKTI_LAUNCH((amg_dense_apply_kernel<double, double>), div_up((int64_t)N * 32, 128), 128, 0, s, N, I.dense.p, I.cglob.p, I.csol.p);
+          if (L.n) SHAKTI_LAUNCH((amg_convert_kernel<double, T>), div_up(L.n, 256), 256, 0, s, L.n, I.csol.p + I.coff_me, v.x.p);
+        } else if (L.n) {
+          SHAKTI_LAUNCH((amg_dense_apply_kernel<T, T>), div_up((int64_t)L.n * 32, 128), 128, 0, s, L.n, I.dense.p, v.b.p, v.x.p);
+        }
+      } else {
+        smooth<T>(I, L, A, v.b.p, 8, true, false);
+      }
+      break;
+    }
+    smooth<T>(I, L, A, v.b.p, I.opt.presmooth, true, false);
+    L.halo->exchange(v.x.p, s);
+    launch_residual<T>(view_as<T>(A), v.x.p, v.b.p, v.r.p, s);
+    launch_spmv<T>(view_as<T>(L.R), v.r.p, vecs<T>(*I.lv[l + 1]).b.p, s);
+  }
+  for (int l = nl - 2; l >= 0; --l) {   // upward
+    AmgLevel& L = *I.lv[l];
+    CycleVecs<T>& v = vecs<T>(L);
+    const DevSell& A = (l == 0) ? Afine : L.A;
+    AmgLevel& C = *I.lv[l + 1];
+    C.halo->exchange(vecs<T>(C).x.p, s);
+    // own rows AND ghost rows of P are applied: the ghost part of x stays consistent with its owner
+    // (it was exchanged before the residual), so the first post-smoothing step needs no exchange
+    launch_spmv_add<T>(view_as<T>(L.P), vecs<T>(C).x.p, v.x.p, s);
+    smooth<T>(I, L, A, v.b.p, I.opt.postsmooth, false, true);
   }
 }
 
 void Amg::apply(const DevSell& Afine, const double* rin, double* z) {
   Impl& I = *p_;
   cudaStream_t s = I.s;
-  const int nl = (int)I.lv.size();
-  for (int l = 0; l < nl; ++l) {   // downward
-    AmgLevel& L = *I.lv[l];
-    const DevSell& A = (l == 0) ? Afine : L.A;
-    const double* b = (l == 0) ? rin : L.b.p;
-    if (L.last) {
-      if (I.dense_coarse) {
-        const int32_t N = I.cN, nmax = std::max(I.cnmax, 1);
-        if (comm().active()) {
-          SHAKTI_CUDA(cudaMemsetAsync(I.crhs.p, 0, sizeof(double) * nmax, s));
-          if (L.n) SHAKTI_CUDA(cudaMemcpyAsync(I.crhs.p, b, sizeof(double) * L.n, cudaMemcpyDeviceToDevice, s));
-          comm_allgather(I.crhs.p, I.cgather.p, nmax, s);
-          SHAKTI_LAUNCH(amg_compact_kernel, div_up(N, 128), 128, 0, s, N, nmax, comm().nranks, I.coff.p, I.cgather.p, I.cglob.p);
-          SHAKTI_LAUNCH(amg_dense_apply_kernel, div_up((int64_t)N * 32, 128), 128, 0, s, N, I.dense.p, I.cglob.p, I.csol.p);
-          if (L.n) SHAKTI_CUDA(cudaMemcpyAsync(L.x.p, I.csol.p + I.coff_me, sizeof(double) * L.n, cudaMemcpyDeviceToDevice, s));
-        } else if (L.n) {
-          SHAKTI_LAUNCH(amg_dense_apply_kernel, div_up((int64_t)L.n * 32, 128), 128, 0, s, L.n, I.dense.p, b, L.x.p);
-        }
-      } else {
-        smooth(I, L, A, b, 8, true);
-      }
-      break;
-    }
-    smooth(I, L, A, b, I.opt.presmooth, true);
-    L.halo->exchange(L.x.p, s);
-    launch_residual(view(A), L.x.p, b, L.r.p, s);
-    launch_spmv(view(L.R), L.r.p, I.lv[l + 1]->b.p, s);
-  }
-  for (int l = nl - 2; l >= 0; --l) {   // upward
-    AmgLevel& L = *I.lv[l];
-    const DevSell& A = (l == 0) ? Afine : L.A;
-    const double* b = (l == 0) ? rin : L.b.p;
-    AmgLevel& C = *I.lv[l + 1];
-    C.halo->exchange(C.x.p, s);
-    // own rows and ghost rows of P: the ghost part of x comes out consistent with its owner
-    launch_spmv_add(view(L.P), C.x.p, L.x.p, s);
-    smooth(I, L, A, b, I.opt.postsmooth, false);
-  }
   AmgLevel& L0 = *I.lv[0];
-  if (L0.n) SHAKTI_CUDA(cudaMemcpyAsync(z, L0.x.p, sizeof(double) * L0.n, cudaMemcpyDeviceToDevice, s));
+  if (I.opt.fp32_cycle) {
+    launch_d2f(L0.n, rin, L0.vf.b.p, s);
+    vcycle<float>(I, Afine);
+    launch_f2d(L0.n, L0.vf.x.p, z, s);
+  } else {
+    if (L0.n) SHAKTI_CUDA(cudaMemcpyAsync(L0.vd.b.p, rin, sizeof(double) * L0.n, cudaMemcpyDeviceToDevice, s));
+    vcycle<double>(I, Afine);
+    if (L0.n) SHAKTI_CUDA(cudaMemcpyAsync(z, L0.vd.x.p, sizeof(double) * L0.n, cudaMemcpyDeviceToDevice, s));
+  }
 }
 
 }  // namespace shakti

@@ -21,6 +21,7 @@ struct AmgOptions {
   double strength_theta = 0.08; // |a_ij| >= theta 0.5^level sqrt(|a_ii a_jj|) is a strong connection (0: all)
   int smoother = 1;             // 0 damped Jacobi (presmooth/postsmooth sweeps), 1 Chebyshev (degree = sweeps)
   double cheby_ratio = 5.0;     // Chebyshev interval [lmax/ratio, lmax] of D^-1 A
+  int fp32_cycle = 1;           // 1: V-cycle in single precision (set-up and Krylov stay fp64)
 };
 
 class Amg {

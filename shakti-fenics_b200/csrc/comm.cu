@@ -12,7 +12,7 @@ namespace shakti {
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 enum { ncclSuccess = 0 };
-enum { ncclFloat64 = 8 };  // ncclDataType_t: ncclDouble
+enum { ncclFloat32 = 7, ncclFloat64 = 8 };  // ncclDataType_t
 enum { ncclSum = 0, ncclMax = 2 };
 
 struct NcclApi {
@@ -246,6 +246,24 @@ void HaloPlan::exchange_packed(const double* sendbuf, double* recvbuf, int32_t g
     if (p.recv_cnt)
       SHAKTI_NCCL(g_api.Recv(recvbuf + (size_t)(p.recv_begin - ghost_base) * width, (size_t)p.recv_cnt * width, ncclFloat64,
                              p.rank, g_nccl, s));
+  }
+  SHAKTI_NCCL(g_api.GroupEnd());
+}
+
+__global__ void halo_gather_f32_kernel(int32_t n, const int32_t* __restrict__ idx, const float* __restrict__ v,
+                                       float* __restrict__ out) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = v[idx[i]];
+}
+
+void HaloPlan::exchange(float* v, cudaStream_t s) {
+  if (!g_comm.active() || peers.empty()) return;
+  if (send_buf_f.n < (size_t)n_send) send_buf_f.alloc((size_t)std::max(n_send, 1));
+  if (n_send) SHAKTI_LAUNCH(halo_gather_f32_kernel, div_up(n_send, 256), 256, 0, s, n_send, send_idx.p, v, send_buf_f.p);
+  SHAKTI_NCCL(g_api.GroupStart());
+  for (const auto& p : peers) {
+    if (p.send_cnt) SHAKTI_NCCL(g_api.Send(send_buf_f.p + p.send_off, (size_t)p.send_cnt, ncclFloat32, p.rank, g_nccl, s));
+    if (p.recv_cnt) SHAKTI_NCCL(g_api.Recv(v + p.recv_begin, (size_t)p.recv_cnt, ncclFloat32, p.rank, g_nccl, s));
   }
   SHAKTI_NCCL(g_api.GroupEnd());
 }

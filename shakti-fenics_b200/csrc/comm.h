@@ -34,11 +34,13 @@ struct HaloPlan {
   struct Peer { int rank; int32_t send_off, send_cnt, recv_begin, recv_cnt; };
   std::vector<Peer> peers;
   DevBuf<int32_t> send_idx;   // concatenated owned local ids to pack
-  DevBuf<double> send_buf;    // up to 4 fields packed
+  DevBuf<double> send_buf;
+  DevBuf<float> send_buf_f;
   int32_t n_send = 0;
   void build(const std::vector<Neighbor>& nbrs);
   // v: n_local vector; ghosts [recv_begin, ...) are overwritten with the owners' values
   void exchange(double* v, cudaStream_t s);
+  void exchange(float* v, cudaStream_t s);
   // same for `width` doubles per vertex, v laid out [vertex][width]
   void exchange_block(double* v, int width, cudaStream_t s);
   // pre-packed variant: `sendbuf` holds width doubles per entry of the send list (in send-list

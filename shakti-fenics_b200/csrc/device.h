@@ -22,16 +22,24 @@ struct DevSell {
   int64_t padded = 0, nnz = 0;
   DevBuf<int32_t> slice_ptr, col, rowlen;
   DevBuf<double> val;
+  mutable DevBuf<float> valf;   // single-precision copy of val (mixed-precision AMG cycle), made on demand
   void upload_pattern(const HostSell& h, int64_t nnz_);
+  void refresh_f32(cudaStream_t s) const;   // valf <- val
 };
 
-struct SellView {
+template <class T>
+struct SellViewT {
   int32_t n_rows, n_slices;
   const int32_t* slice_ptr;
   const int32_t* col;
-  const double* val;
+  const T* val;
 };
+using SellView = SellViewT<double>;
 inline SellView view(const DevSell& a) { return {a.n_rows, a.n_slices, a.slice_ptr.p, a.col.p, a.val.p}; }
+inline SellViewT<float> viewf(const DevSell& a) { return {a.n_rows, a.n_slices, a.slice_ptr.p, a.col.p, a.valf.p}; }
+template <class T> inline SellViewT<T> view_as(const DevSell& a);
+template <> inline SellViewT<double> view_as<double>(const DevSell& a) { return view(a); }
+template <> inline SellViewT<float> view_as<float>(const DevSell& a) { return viewf(a); }
 
 // Pointers of the vertex fields the element kernels read (all n_local long)
 struct FieldPtrs {
@@ -77,13 +85,16 @@ void launch_update_b(int32_t n_owned, const int32_t* win, const double* x, const
                      const double* qy, const double* G, const double* melt, double* b_new, double dt,
                      double b_min, DevParams p, cudaStream_t s);
 
-// ---- sparse / vector kernels
-void launch_spmv(SellView A, const double* x, double* y, cudaStream_t s);                      // y = A x
-void launch_residual(SellView A, const double* x, const double* b, double* r, cudaStream_t s); // r = b - A x
+// ---- sparse / vector kernels (T = double, or float for the mixed-precision AMG cycle)
+template <class T> void launch_spmv(SellViewT<T> A, const T* x, T* y, cudaStream_t s);                 // y = A x
+template <class T> void launch_residual(SellViewT<T> A, const T* x, const T* b, T* r, cudaStream_t s); // r = b - A x
 // x_out = x + omega * dinv .* (b - A x)
-void launch_jacobi(SellView A, const double* dinv, const double* b, const double* x, double* x_out,
-                   double omega, cudaStream_t s);
-void launch_spmv_add(SellView A, const double* x, double* y, cudaStream_t s);                  // y += A x
+template <class T> void launch_jacobi(SellViewT<T> A, const T* dinv, const T* b, const T* x, T* x_out, double omega, cudaStream_t s);
+template <class T> void launch_spmv_add(SellViewT<T> A, const T* x, T* y, cudaStream_t s);             // y += A x
+template <class T> void launch_scaled_mul(int64_t n, const T* a, const T* b, double scale, T* out, cudaStream_t s);  // out = scale a.*b
+template <class T> void launch_fill_t(int64_t n, T v, T* x, cudaStream_t s);
+void launch_d2f(int64_t n, const double* a, float* out, cudaStream_t s);
+void launch_f2d(int64_t n, const float* a, double* out, cudaStream_t s);
 void launch_extract_dinv(int32_t n, const int32_t* diag_pos, const double* val, double* dinv, cudaStream_t s);
 
 // reductions: out[k] = <V_k, w>, V_k = V + k*ld, k < nvec; result in device memory `out`

@@ -555,18 +555,18 @@ void launch_update_b(int32_t n_owned, const int32_t* win, const double* x, const
 // ordered, neighbours are close in memory).
 enum { SPMV_SET = 0, SPMV_ADD = 1, SPMV_RESID = 2, SPMV_JACOBI = 3 };
 
-template <int MODE>
+template <int MODE, class T>
 __global__ void __launch_bounds__(256)
-spmv_sell_kernel(SellView A, const double* __restrict__ x, const double* __restrict__ b,
-                 const double* __restrict__ dinv, double omega, double* __restrict__ y) {
+spmv_sell_kernel(SellViewT<T> A, const T* __restrict__ x, const T* __restrict__ b, const T* __restrict__ dinv, T omega,
+                 T* __restrict__ y) {
   const int32_t row = blockIdx.x * blockDim.x + threadIdx.x;
   const int32_t slice = row >> 5;
   if (slice >= A.n_slices) return;
   const int32_t base = A.slice_ptr[slice];
   const int32_t w = (A.slice_ptr[slice + 1] - base) >> 5;
   const int32_t* __restrict__ cp = A.col + base + (row & 31);
-  const double* __restrict__ vp = A.val + base + (row & 31);
-  double acc = 0.0;
+  const T* __restrict__ vp = A.val + base + (row & 31);
+  T acc = 0;
 #pragma unroll 4
   for (int k = 0; k < w; ++k) acc += vp[32 * k] * x[cp[32 * k]];
   if (row >= A.n_rows) return;
@@ -576,18 +576,69 @@ spmv_sell_kernel(SellView A, const double* __restrict__ x, const double* __restr
   else y[row] = x[row] + omega * dinv[row] * (b[row] - acc);
 }
 
-template <int MODE>
-static void spmv_launch(SellView A, const double* x, const double* b, const double* dinv, double omega,
-                        double* y, cudaStream_t s) {
+template <int MODE, class T>
+static void spmv_launch(SellViewT<T> A, const T* x, const T* b, const T* dinv, double omega, T* y, cudaStream_t s) {
   if (A.n_rows == 0) return;
   const int64_t threads = (int64_t)A.n_slices * 32;
-  SHAKTI_LAUNCH(spmv_sell_kernel<MODE>, div_up(threads, 256), 256, 0, s, A, x, b, dinv, omega, y);
+  SHAKTI_LAUNCH((spmv_sell_kernel<MODE, T>), div_up(threads, 256), 256, 0, s, A, x, b, dinv, (T)omega, y);
 }
-void launch_spmv(SellView A, const double* x, double* y, cudaStream_t s) { spmv_launch<SPMV_SET>(A, x, nullptr, nullptr, 0, y, s); }
-void launch_spmv_add(SellView A, const double* x, double* y, cudaStream_t s) { spmv_launch<SPMV_ADD>(A, x, nullptr, nullptr, 0, y, s); }
-void launch_residual(SellView A, const double* x, const double* b, double* r, cudaStream_t s) { spmv_launch<SPMV_RESID>(A, x, b, nullptr, 0, r, s); }
-void launch_jacobi(SellView A, const double* dinv, const double* b, const double* x, double* x_out, double omega,
-                   cudaStream_t s) { spmv_launch<SPMV_JACOBI>(A, x, b, dinv, omega, x_out, s); }
+template <class T> void launch_spmv(SellViewT<T> A, const T* x, T* y, cudaStream_t s) { spmv_launch<SPMV_SET, T>(A, x, nullptr, nullptr, 0, y, s); }
+template <class T> void launch_spmv_add(SellViewT<T> A, const T* x, T* y, cudaStream_t s) { spmv_launch<SPMV_ADD, T>(A, x, nullptr, nullptr, 0, y, s); }
+template <class T> void launch_residual(SellViewT<T> A, const T* x, const T* b, T* r, cudaStream_t s) { spmv_launch<SPMV_RESID, T>(A, x, b, nullptr, 0, r, s); }
+template <class T> void launch_jacobi(SellViewT<T> A, const T* dinv, const T* b, const T* x, T* x_out, double omega, cudaStream_t s) {
+  spmv_launch<SPMV_JACOBI, T>(A, x, b, dinv, omega, x_out, s);
+}
+#define SHAKTI_INSTANTIATE_SPMV(T)                                                                       \
+  template void launch_spmv<T>(SellViewT<T>, const T*, T*, cudaStream_t);                                \
+  template void launch_spmv_add<T>(SellViewT<T>, const T*, T*, cudaStream_t);                            \
+  template void launch_residual<T>(SellViewT<T>, const T*, const T*, T*, cudaStream_t);                  \
+  template void launch_jacobi<T>(SellViewT<T>, const T*, const T*, const T*, T*, double, cudaStream_t);
+SHAKTI_INSTANTIATE_SPMV(double)
+SHAKTI_INSTANTIATE_SPMV(float)
+
+__global__ void d2f_kernel(int64_t n, const double* __restrict__ a, float* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (float)a[i];
+}
+__global__ void f2d_kernel(int64_t n, const float* __restrict__ a, double* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (double)a[i];
+}
+static int conv_blocks(int64_t n) { return (int)std::min<int64_t>(148 * 16, std::max<int64_t>(1, (n + 255) / 256)); }
+void launch_d2f(int64_t n, const double* a, float* out, cudaStream_t s) {
+  if (n == 0) return;
+  SHAKTI_LAUNCH(d2f_kernel, conv_blocks(n), 256, 0, s, n, a, out);
+}
+void launch_f2d(int64_t n, const float* a, double* out, cudaStream_t s) {
+  if (n == 0) return;
+  SHAKTI_LAUNCH(f2d_kernel, conv_blocks(n), 256, 0, s, n, a, out);
+}
+void DevSell::refresh_f32(cudaStream_t s) const {
+  if (valf.n != (size_t)padded) valf.alloc((size_t)padded);
+  launch_d2f(padded, val.p, valf.p, s);
+}
+template <class T>
+__global__ void scaled_mul_kernel(int64_t n, const T* __restrict__ a, const T* __restrict__ b, T scale, T* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = scale * a[i] * b[i];
+}
+template <class T> void launch_scaled_mul(int64_t n, const T* a, const T* b, double scale, T* out, cudaStream_t s) {
+  if (n == 0) return;
+  SHAKTI_LAUNCH((scaled_mul_kernel<T>), conv_blocks(n), 256, 0, s, n, a, b, (T)scale, out);
+}
+template void launch_scaled_mul<double>(int64_t, const double*, const double*, double, double*, cudaStream_t);
+template void launch_scaled_mul<float>(int64_t, const float*, const float*, double, float*, cudaStream_t);
+template <class T>
+__global__ void fill_t_kernel(int64_t n, T v, T* __restrict__ x) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] = v;
+}
+template <class T> void launch_fill_t(int64_t n, T v, T* x, cudaStream_t s) {
+  if (n == 0) return;
+  SHAKTI_LAUNCH((fill_t_kernel<T>), conv_blocks(n), 256, 0, s, n, v, x);
+}
+template void launch_fill_t<double>(int64_t, double, double*, cudaStream_t);
+template void launch_fill_t<float>(int64_t, float, float*, cudaStream_t);
 
 __global__ void extract_dinv_kernel(int32_t n, const int32_t* __restrict__ diag_pos, const double* __restrict__ val,
                                     double* __restrict__ dinv) {

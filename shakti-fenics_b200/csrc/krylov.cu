@@ -72,6 +72,9 @@ void Gmres::init(int64_t n_owned, int64_t n_local, int restart, int sm_count, cu
   ld_ = ((n_owned + 31) / 32) * 32;
   if (ld_ == 0) ld_ = 32;
   V_.alloc_zero((size_t)(m_ + 1) * ld_, s);
+  ldz_ = ((n_local + 31) / 32) * 32;
+  if (ldz_ == 0) ldz_ = 32;
+  Z_.alloc_zero((size_t)m_ * ldz_, s);   // flexible variant: z_j = M^-1 v_j kept (n_local long: the operator fills ghosts)
   z_.alloc_zero(std::max<int64_t>(n_local, 1), s);
   u_.alloc_zero(ld_, s);
   r_.alloc_zero(ld_, s);
@@ -123,8 +126,9 @@ KrylovResult Gmres::solve(const ApplyFn& A, const PrecFn& M, const AllReduceFn& 
     bool done = false;
     for (int j = 0; j < m_; ++j) {
       double* w = V_.p + (size_t)(j + 1) * ld_;
-      M(V_.p + (size_t)j * ld_, z_.p);
-      A(z_.p, w);
+      double* zj = Z_.p + (size_t)j * ldz_;
+      M(V_.p + (size_t)j * ld_, zj);
+      A(zj, w);
       launch_multi_dot(red_, n_, j + 1, V_.p, ld_, w, h_, s_);
       allreduce(h_, j + 1);
       launch_multi_axpy_neg(n_, j + 1, V_.p, ld_, h_, w, s_);
@@ -143,9 +147,8 @@ KrylovResult Gmres::solve(const ApplyFn& A, const PrecFn& M, const AllReduceFn& 
       launch_scale_dev(n_, w, scal_ + 2, 1, w, s_);
     }
     SHAKTI_LAUNCH(gmres_solve_y_kernel, 1, 1, 0, s_, k, m_, H_, g_, y_);
-    launch_combine(n_, k, V_.p, ld_, y_, u_.p, s_);
-    M(u_.p, z_.p);
-    launch_axpy(n_, 1.0, z_.p, x, s_);
+    launch_combine(n_, k, Z_.p, ldz_, y_, u_.p, s_);     // x += Z y: no extra preconditioner application,
+    launch_axpy(n_, 1.0, u_.p, x, s_);                   // and exact even if M^-1 is only approximately linear
     res.relres = bnorm > 0 ? resid / bnorm : 0.0;
     if (done && (resid <= tol || !std::isfinite(resid))) {
       res.converged = std::isfinite(resid);

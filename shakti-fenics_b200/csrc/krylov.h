@@ -1,4 +1,4 @@
-// Right-preconditioned restarted GMRES with device-resident Hessenberg/Givens state.
+// Flexible right-preconditioned restarted GMRES (FGMRES) with device-resident Hessenberg/Givens state.
 // Replaces PETSc KSP(preonly)+PC(lu) behind DOLFINx NewtonSolver (reference solvers.py:52,179).
 #pragma once
 #include <functional>
@@ -30,10 +30,10 @@ class Gmres {
   Reducer& reducer() { return red_; }
 
  private:
-  int64_t n_ = 0, nl_ = 0, ld_ = 0;
+  int64_t n_ = 0, nl_ = 0, ld_ = 0, ldz_ = 0;
   int m_ = 0;
   cudaStream_t s_ = 0;
-  DevBuf<double> V_, z_, u_, r_, small_;
+  DevBuf<double> V_, Z_, z_, u_, r_, small_;
   Reducer red_;
   double* host_status_ = nullptr;  // pinned: [0] = residual estimate, [1] = beta
   // layout of small_: h[m+2] h2[m+2] H[(m+1)*m] cs[m] sn[m] g[m+1] y[m] scal[4]

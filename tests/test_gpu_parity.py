@@ -56,10 +56,11 @@ def test_spmv(case):
     assert relinf(y, o.jacobian_matrix(Jo) @ x) < 1e-13
 
 
-@pytest.mark.parametrize("ksp,pc", [("gmres", "jacobi"), ("gmres", "amg"), ("bicgstab", "jacobi"), ("bicgstab", "amg")])
-def test_linear_solve(case, ksp, pc):
+@pytest.mark.parametrize("ksp,pc,fp32", [("gmres", "jacobi", 1), ("gmres", "amg", 1), ("gmres", "amg", 0),
+                                         ("bicgstab", "jacobi", 1), ("bicgstab", "amg", 1), ("bicgstab", "amg", 0)])
+def test_linear_solve(case, ksp, pc, fp32):
     _, o, m = case
-    m.set_options(linear_solver=ksp, precond=pc, linear_rtol=1e-12, linear_max_it=5000)
+    m.set_options(linear_solver=ksp, precond=pc, linear_rtol=1e-12, linear_max_it=5000, amg_fp32_cycle=fp32)
     m.assemble(DT)
     Fo, Jo = o.assemble(DT)
     A = o.jacobian_matrix(Jo).tocsc()
