@@ -735,11 +735,11 @@ void launch_multi_dot(Reducer& red, int64_t n, int nvec, const double* V, int64_
 }
 
 // w -= sum_k h[k] V_k  (SUB) or y = sum_k h[k] V_k (SET, first chunk) / y += ... (ADD)
-enum { COMB_SUB = 0, COMB_SET = 1, COMB_ADD = 2 };
+enum { COMB_SUB = 0, COMB_SET = 1, COMB_ADD = 2, COMB_SUB_SCALE = 3 };
 template <int NV, int MODE>
 __global__ void __launch_bounds__(256)
 combine_kernel(int64_t n, const double* __restrict__ V, int64_t ld, const double* __restrict__ h,
-               double* __restrict__ w) {
+               double* __restrict__ w, double scale) {
   double hk[NV];
 #pragma unroll
   for (int k = 0; k < NV; ++k) hk[k] = h[k];
@@ -750,22 +750,23 @@ combine_kernel(int64_t n, const double* __restrict__ V, int64_t ld, const double
     for (int k = 0; k < NV; ++k) acc += hk[k] * V[k * ld + i];
     if (MODE == COMB_SUB) w[i] -= acc;
     else if (MODE == COMB_SET) w[i] = acc;
-    else w[i] += acc;
+    else if (MODE == COMB_ADD) w[i] += acc;
+    else w[i] = (w[i] - acc) * scale;
   }
 }
 
 template <int MODE>
 static void combine_chunk(int c, int blocks, int64_t n, const double* V, int64_t ld, const double* h, double* w,
-                          cudaStream_t s) {
+                          cudaStream_t s, double scale = 1.0) {
   switch (c) {
-    case 1: SHAKTI_LAUNCH((combine_kernel<1, MODE>), blocks, 256, 0, s, n, V, ld, h, w); break;
-    case 2: SHAKTI_LAUNCH((combine_kernel<2, MODE>), blocks, 256, 0, s, n, V, ld, h, w); break;
-    case 3: SHAKTI_LAUNCH((combine_kernel<3, MODE>), blocks, 256, 0, s, n, V, ld, h, w); break;
-    case 4: SHAKTI_LAUNCH((combine_kernel<4, MODE>), blocks, 256, 0, s, n, V, ld, h, w); break;
-    case 5: SHAKTI_LAUNCH((combine_kernel<5, MODE>), blocks, 256, 0, s, n, V, ld, h, w); break;
-    case 6: SHAKTI_LAUNCH((combine_kernel<6, MODE>), blocks, 256, 0, s, n, V, ld, h, w); break;
-    case 7: SHAKTI_LAUNCH((combine_kernel<7, MODE>), blocks, 256, 0, s, n, V, ld, h, w); break;
-    default: SHAKTI_LAUNCH((combine_kernel<8, MODE>), blocks, 256, 0, s, n, V, ld, h, w); break;
+    case 1: SHAKTI_LAUNCH((combine_kernel<1, MODE>), blocks, 256, 0, s, n, V, ld, h, w, scale); break;
+    case 2: SHAKTI_LAUNCH((combine_kernel<2, MODE>), blocks, 256, 0, s, n, V, ld, h, w, scale); break;
+    case 3: SHAKTI_LAUNCH((combine_kernel<3, MODE>), blocks, 256, 0, s, n, V, ld, h, w, scale); break;
+    case 4: SHAKTI_LAUNCH((combine_kernel<4, MODE>), blocks, 256, 0, s, n, V, ld, h, w, scale); break;
+    case 5: SHAKTI_LAUNCH((combine_kernel<5, MODE>), blocks, 256, 0, s, n, V, ld, h, w, scale); break;
+    case 6: SHAKTI_LAUNCH((combine_kernel<6, MODE>), blocks, 256, 0, s, n, V, ld, h, w, scale); break;
+    case 7: SHAKTI_LAUNCH((combine_kernel<7, MODE>), blocks, 256, 0, s, n, V, ld, h, w, scale); break;
+    default: SHAKTI_LAUNCH((combine_kernel<8, MODE>), blocks, 256, 0, s, n, V, ld, h, w, scale); break;
   }
 }
 static int stream_blocks(int64_t n) { return (int)std::min<int64_t>(148 * 16, std::max<int64_t>(1, (n + 255) / 256)); }
@@ -775,6 +776,16 @@ void launch_multi_axpy_neg(int64_t n, int nvec, const double* V, int64_t ld, con
   if (n == 0) return;
   for (int done = 0; done < nvec; done += 8)
     combine_chunk<COMB_SUB>(std::min(8, nvec - done), stream_blocks(n), n, V + (int64_t)done * ld, ld, h + done, w, s);
+}
+// w = (w - sum_k h[k] V_k) * scale : Gram-Schmidt update fused with the normalisation
+void launch_multi_axpy_neg_scale(int64_t n, int nvec, const double* V, int64_t ld, const double* h, double* w, double scale,
+                                 cudaStream_t s) {
+  if (n == 0) return;
+  for (int done = 0; done < nvec; done += 8) {
+    const int c = std::min(8, nvec - done);
+    if (done + c >= nvec) combine_chunk<COMB_SUB_SCALE>(c, stream_blocks(n), n, V + (int64_t)done * ld, ld, h + done, w, s, scale);
+    else combine_chunk<COMB_SUB>(c, stream_blocks(n), n, V + (int64_t)done * ld, ld, h + done, w, s);
+  }
 }
 void launch_combine(int64_t n, int nvec, const double* V, int64_t ld, const double* h, double* y, cudaStream_t s) {
   if (n == 0) return;
