@@ -109,6 +109,9 @@ void launch_multi_dot(Reducer& red, int64_t n, int nvec, const double* V, int64_
 // w -= sum_k h[k] V_k   (h on device)
 void launch_multi_axpy_neg(int64_t n, int nvec, const double* V, int64_t ld, const double* h, double* w,
                            cudaStream_t s);
+// fused: w -= V h; out[0..nvec) = V^T w_new; out[nvec] = <w_new,w_new>.  false: nvec too large, nothing done
+bool launch_orth_update_dot(Reducer& red, int64_t n, int nvec, const double* V, int64_t ld, const double* h, double* w,
+                            double* out, cudaStream_t s);
 void launch_multi_axpy_neg_scale(int64_t n, int nvec, const double* V, int64_t ld, const double* h, double* w, double scale,
                                  cudaStream_t s);
 // y = sum_k h[k] V_k

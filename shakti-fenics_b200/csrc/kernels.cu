@@ -657,7 +657,7 @@ constexpr int kRedThreads = 256;
 
 void Reducer::init(int sm_count) {
   max_blocks = sm_count * 8;
-  partial.alloc((size_t)max_blocks * 8);
+  partial.alloc((size_t)max_blocks * 32);
   counter.alloc_zero(1);
 }
 
@@ -732,6 +732,77 @@ void launch_multi_dot(Reducer& red, int64_t n, int nvec, const double* V, int64_
     }
     done += c;
   }
+}
+
+// Second classical Gram-Schmidt pass fused with the first pass's update:
+//   w <- w - sum_k h[k] V_k ;  out[k] = <V_k, w_new> (k < nvec) ;  out[nvec] = <w_new, w_new>
+// The basis is read once for both.  nvec <= NV; deterministic two-stage reduction as in multi_dot.
+template <int NV>
+__global__ void __launch_bounds__(kRedThreads)
+orth_update_dot_kernel(int64_t n, int nvec, const double* __restrict__ V, int64_t ld, const double* __restrict__ h,
+                       double* __restrict__ w, double* __restrict__ partial, unsigned int* __restrict__ counter,
+                       double* __restrict__ out) {
+  double hk[NV], acc[NV + 1];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) { hk[k] = k < nvec ? h[k] : 0.0; acc[k] = 0.0; }
+  acc[NV] = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double vk[NV];
+    double a = 0.0;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      vk[k] = k < nvec ? V[k * ld + i] : 0.0;
+      a += hk[k] * vk[k];
+    }
+    const double wn = w[i] - a;
+    w[i] = wn;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc[k] += vk[k] * wn;
+    acc[NV] += wn * wn;
+  }
+  __shared__ double sm[NV + 1][kRedThreads / 32];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k <= NV; ++k) {
+    const double v = warp_sum(acc[k]);
+    if (lane == 0) sm[k][wid] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x <= NV) {
+    double v = 0.0;
+#pragma unroll
+    for (int j = 0; j < kRedThreads / 32; ++j) v += sm[threadIdx.x][j];
+    partial[(size_t)blockIdx.x * (NV + 1) + threadIdx.x] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  for (int k = wid; k <= NV; k += kRedThreads / 32) {
+    double v = 0.0;
+    for (int b = lane; b < (int)gridDim.x; b += 32) v += partial[(size_t)b * (NV + 1) + k];
+    v = warp_sum(v);
+    if (lane == 0) {
+      if (k < nvec) out[k] = v;
+      else if (k == NV) out[nvec] = v;
+    }
+  }
+  if (threadIdx.x == 0) *counter = 0u;
+}
+
+// returns false if nvec is too large for the fused kernel (caller falls back to separate passes)
+bool launch_orth_update_dot(Reducer& red, int64_t n, int nvec, const double* V, int64_t ld, const double* h, double* w,
+                            double* out, cudaStream_t s) {
+  if (nvec > 24) return false;
+  const int blocks = (int)std::min<int64_t>(red.max_blocks, std::max<int64_t>(1, (n + kRedThreads * 4 - 1) / (kRedThreads * 4)));
+  if (nvec <= 8) SHAKTI_LAUNCH(orth_update_dot_kernel<8>, blocks, kRedThreads, 0, s, n, nvec, V, ld, h, w, red.partial.p, red.counter.p, out);
+  else if (nvec <= 16) SHAKTI_LAUNCH(orth_update_dot_kernel<16>, blocks, kRedThreads, 0, s, n, nvec, V, ld, h, w, red.partial.p, red.counter.p, out);
+  else SHAKTI_LAUNCH(orth_update_dot_kernel<24>, blocks, kRedThreads, 0, s, n, nvec, V, ld, h, w, red.partial.p, red.counter.p, out);
+  return true;
 }
 
 // w -= sum_k h[k] V_k  (SUB) or y = sum_k h[k] V_k (SET, first chunk) / y += ... (ADD)

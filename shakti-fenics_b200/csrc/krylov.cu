@@ -95,7 +95,7 @@ void Gmres::init(int64_t n_owned, int64_t n_local, int restart, int sm_count, cu
   scal_ = p;
   red_.init(sm_count);
   if (host_status_) { cudaFreeHost(host_status_); host_status_ = nullptr; }
-  SHAKTI_CUDA(cudaMallocHost(&host_status_, (m_ + 8) * sizeof(double)));
+  SHAKTI_CUDA(cudaMallocHost(&host_status_, (2 * m_ + 16) * sizeof(double)));
 }
 
 Gmres::~Gmres() {
@@ -104,11 +104,11 @@ Gmres::~Gmres() {
 
 KrylovResult Gmres::solve(const ApplyFn& A, const PrecFn& M, const AllReduceFn& allreduce, const double* b,
                           double* x, double rtol, double atol, int max_it) {
-  // Per iteration: preconditioner, operator, ONE fused multi-dot pass over the basis (h = V^T w and
-  // <w,w> together), one host read of those j+2 numbers, and ONE pass that subtracts V h and
-  // normalises.  The new direction's norm follows from Pythagoras; when that cancels (DGKS
-  // criterion) the classical Gram-Schmidt step is repeated.  The (m+1) x m Hessenberg algebra
-  // (Givens rotations, residual estimate, back substitution) runs on the host on those numbers.
+  // Per iteration: preconditioner, operator, classical Gram-Schmidt applied twice in three passes
+  // over the basis (see below), ONE host read of the 2(j+2) coefficients.  With a strong
+  // preconditioner w ~ v_j, so the second pass is always needed (measured: dropping it raises the
+  // iteration count by 40 %).  The (m+1) x m Hessenberg algebra (Givens rotations, residual
+  // estimate, back substitution) runs on the host on those numbers.
   KrylovResult res;
   std::vector<double> H((size_t)(m_ + 1) * m_, 0.0), cs(m_, 0.0), sn(m_, 0.0), g(m_ + 1, 0.0), y(m_, 0.0), hh(m_ + 2, 0.0);
   double* hbuf = host_status_;    // pinned, m_ + 2 doubles
@@ -145,26 +145,21 @@ KrylovResult Gmres::solve(const ApplyFn& A, const PrecFn& M, const AllReduceFn& 
       double* zj = Z_.p + (size_t)j * ldz_;
       M(V_.p + (size_t)j * ld_, zj);
       A(zj, w);
-      launch_multi_dot(red_, n_, j + 2, V_.p, ld_, w, h_, s_);   // h[0..j] = <v_i, w>, h[j+1] = <w, w>
-      allreduce(h_, j + 2);
-      read(h_, j + 2);
-      double s2 = 0.0;
-      for (int i = 0; i <= j; ++i) { hh[i] = hbuf[i]; s2 += hbuf[i] * hbuf[i]; }
-      double ww = hbuf[j + 1], rem = ww - s2;
-      const double* hdev = h_;
-      // DGKS criterion.  (Measured: relaxing it to rem/ww < 1e-3 raised the iteration count from 15 to 21 per solve,
-      // so with a strong preconditioner, where w ~ v_j, the second pass is the rule, not the exception.)
-      if (!(rem > 0.5 * ww)) {
+      // classical Gram-Schmidt twice (CGS2) in three passes over the basis:
+      //   1. h = V^T w                       2. w -= V h fused with h2 = V^T w, <w,w>      3. w = (w - V h2)/||.||
+      launch_multi_dot(red_, n_, j + 1, V_.p, ld_, w, h_, s_);
+      allreduce(h_, j + 1);
+      if (!launch_orth_update_dot(red_, n_, j + 1, V_.p, ld_, h_, w, h2_, s_)) {
         launch_multi_axpy_neg(n_, j + 1, V_.p, ld_, h_, w, s_);
         launch_multi_dot(red_, n_, j + 2, V_.p, ld_, w, h2_, s_);
-        allreduce(h2_, j + 2);
-        read(h2_, j + 2);
-        s2 = 0.0;
-        for (int i = 0; i <= j; ++i) { hh[i] += hbuf[i]; s2 += hbuf[i] * hbuf[i]; }
-        ww = hbuf[j + 1];
-        rem = ww - s2;
-        hdev = h2_;
       }
+      allreduce(h2_, j + 2);
+      // h and h2 are adjacent in device memory (h_[m+2], h2_[m+2]): one read
+      read(h_, (m_ + 2) + (j + 2));
+      double s2 = 0.0;
+      for (int i = 0; i <= j; ++i) { hh[i] = hbuf[i] + hbuf[m_ + 2 + i]; s2 += hbuf[m_ + 2 + i] * hbuf[m_ + 2 + i]; }
+      const double rem = hbuf[m_ + 2 + j + 1] - s2;   // ||w - V h2||^2 by Pythagoras: h2 is tiny, no cancellation
+      const double* hdev = h2_;
       const double hj1 = std::sqrt(std::max(rem, 0.0));
       // Hessenberg column j, stored rotations, new rotation, residual estimate
       double* col = H.data() + (size_t)j * (m_ + 1);
