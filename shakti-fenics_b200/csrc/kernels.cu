@@ -175,33 +175,72 @@ __device__ __forceinline__ void element_core(const Geo& g, const double h[3], co
   }
   // closure + storage by quadrature
   const double cs = p.inv_rwg / dt;
-  const double e1 = p.n - 1.0, e2 = p.n - 2.0;
   double f0 = 0, f1 = 0, f2 = 0, m00 = 0, m01 = 0, m02 = 0, m11 = 0, m12 = 0, m22 = 0;
-  const int nq = c_nrq;
-  for (int k = 0; k < nq; ++k) {
-    const double l0 = c_rq[4 * k], l1 = c_rq[4 * k + 1], l2 = c_rq[4 * k + 2];
-    const double w = c_rq[4 * k + 3] * g.detabs;
-    const double bq = l0 * bb[0] + l1 * bb[1] + l2 * bb[2];
-    const double Nq = l0 * Nv[0] + l1 * Nv[1] + l2 * Nv[2];
-    const double dq = Nq - (l0 * Nn[0] + l1 * Nn[1] + l2 * Nn[2]);
-    const double sq = (l0 * st[0] + l1 * st[1] + l2 * st[2]) * cs;
-    double clos, dclos;
-    if (p.n_is_3) {
-      const double N2 = Nq * Nq;                  // abs(N)**2
-      clos = p.A * bq * Nq * N2;
-      dclos = p.A * bq * (N2 + Nq * 2.0 * fabs(Nq) * (Nq > 0 ? 1.0 : (Nq < 0 ? -1.0 : 0.0)));
-    } else {
+  if (p.n_is_3) {
+    // n = 3: integrands are polynomials of degree <= 5 -> Radon's 7-point rule, written out by orbit.
+    // A P1 function with nodal values f_i and sum S is  S/3 at the centroid and  a S + (c-a) f_i  at
+    // orbit point i (barycentrics (a,a,c) permuted), so every interpolation is one FMA; the
+    // phi_a, phi_a phi_b weights collapse to  a R + e r_a  and  a^2 D + a e (d_a + d_b) + e^2 delta_ab d_a.
+    const double dqv[3] = {Nv[0] - Nn[0], Nv[1] - Nn[1], Nv[2] - Nn[2]};
+    const double sv[3] = {st[0] * cs, st[1] * cs, st[2] * cs};
+    const double Sb = bb[0] + bb[1] + bb[2], SN = Nv[0] + Nv[1] + Nv[2], Sd = dqv[0] + dqv[1] + dqv[2],
+                 Ss = sv[0] + sv[1] + sv[2];
+    const double A3 = 3.0 * p.A;
+    {  // centroid, weight 9/80
+      const double w = 0.1125 * g.detabs, t = 1.0 / 3.0;
+      const double bq = Sb * t, Nq = SN * t, dq = Sd * t, sq = Ss * t, N2 = Nq * Nq;
+      const double r = w * (p.A * bq * Nq * N2 + sq * dq) * t;
+      const double d = w * (A3 * bq * N2 + sq) * (t * t);
+      f0 = f1 = f2 = r;
+      m00 = m01 = m02 = m11 = m12 = m22 = d;
+    }
+    const double s15 = 3.872983346207417;   // sqrt(15)
+#pragma unroll
+    for (int orb = 0; orb < 2; ++orb) {
+      const double a = orb == 0 ? (6.0 - s15) / 21.0 : (6.0 + s15) / 21.0;
+      const double w = (orb == 0 ? (155.0 - s15) : (155.0 + s15)) * (1.0 / 2400.0) * g.detabs;
+      const double e = 1.0 - 3.0 * a;   // c - a
+      const double ab = a * Sb, aN = a * SN, ad = a * Sd, as = a * Ss;
+      double r[3], d[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const double bq = ab + e * bb[i], Nq = aN + e * Nv[i], dq = ad + e * dqv[i], sq = as + e * sv[i];
+        const double N2 = Nq * Nq;
+        r[i] = w * (p.A * bq * Nq * N2 + sq * dq);
+        d[i] = w * (A3 * bq * N2 + sq);
+      }
+      const double R = a * (r[0] + r[1] + r[2]), D = a * a * (d[0] + d[1] + d[2]);
+      const double ae = a * e, ee = e * e;
+      f0 += R + e * r[0]; f1 += R + e * r[1]; f2 += R + e * r[2];
+      m00 += D + (2.0 * ae + ee) * d[0];
+      m11 += D + (2.0 * ae + ee) * d[1];
+      m22 += D + (2.0 * ae + ee) * d[2];
+      m01 += D + ae * (d[0] + d[1]);
+      m02 += D + ae * (d[0] + d[2]);
+      m12 += D + ae * (d[1] + d[2]);
+    }
+  } else {
+    // general Glen exponent: the closure is not polynomial; use the table in __constant__ memory
+    const double e1 = p.n - 1.0, e2 = p.n - 2.0;
+    const int nq = c_nrq;
+    for (int k = 0; k < nq; ++k) {
+      const double l0 = c_rq[4 * k], l1 = c_rq[4 * k + 1], l2 = c_rq[4 * k + 2];
+      const double w = c_rq[4 * k + 3] * g.detabs;
+      const double bq = l0 * bb[0] + l1 * bb[1] + l2 * bb[2];
+      const double Nq = l0 * Nv[0] + l1 * Nv[1] + l2 * Nv[2];
+      const double dq = Nq - (l0 * Nn[0] + l1 * Nn[1] + l2 * Nn[2]);
+      const double sq = (l0 * st[0] + l1 * st[1] + l2 * st[2]) * cs;
       const double sgn = Nq > 0 ? 1.0 : (Nq < 0 ? -1.0 : 0.0);
       const double p1 = pow(fabs(Nq), e1);
-      clos = p.A * bq * Nq * p1;
-      dclos = p.A * bq * (p1 + Nq * e1 * pow(fabs(Nq), e2) * sgn);
+      const double clos = p.A * bq * Nq * p1;
+      const double dclos = p.A * bq * (p1 + Nq * e1 * pow(fabs(Nq), e2) * sgn);
+      const double r = w * (clos + sq * dq);
+      const double d = w * (dclos + sq);
+      f0 += r * l0; f1 += r * l1; f2 += r * l2;
+      const double d0 = d * l0, d1 = d * l1;
+      m00 += d0 * l0; m01 += d0 * l1; m02 += d0 * l2;
+      m11 += d1 * l1; m12 += d1 * l2; m22 += d * l2 * l2;
     }
-    const double r = w * (clos + sq * dq);
-    const double d = w * (dclos + sq);
-    f0 += r * l0; f1 += r * l1; f2 += r * l2;
-    const double d0 = d * l0, d1 = d * l1;
-    m00 += d0 * l0; m01 += d0 * l1; m02 += d0 * l2;
-    m11 += d1 * l1; m12 += d1 * l2; m22 += d * l2 * l2;
   }
   o.F[0] -= f0; o.F[1] -= f1; o.F[2] -= f2;
   o.J[0][0] -= m00; o.J[0][1] -= m01; o.J[0][2] -= m02;
@@ -408,7 +447,8 @@ void launch_assemble_blocks(const AssemblyPlanView& pl, FieldPtrs f, const doubl
     SHAKTI_CUDA(cudaFuncSetAttribute(assemble_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  SHAKTI_LAUNCH(assemble_blocks_kernel, pl.n_blocks, 256, smem, s, pl.n_owned, pl.rows_per_block, pl.cap, pl.vcap,
+  const int threads = pl.rows_per_block >= 256 ? 256 : 128;   // phase 2 needs one thread per row
+  SHAKTI_LAUNCH(assemble_blocks_kernel, pl.n_blocks, threads, smem, s, pl.n_owned, pl.rows_per_block, pl.cap, pl.vcap,
                 pl.blk_eptr, pl.blk_elems, pl.blk_lv, pl.blk_hptr, pl.blk_halo, pl.inc_ptr, pl.inc_code, pl.src, f, kbar, dt,
                 N_bdry, slice_ptr, F, Jval, want_J, p);
 }

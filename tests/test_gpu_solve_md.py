@@ -98,3 +98,27 @@ def test_pde_solver_object(tmp_path):
     solver.rtol = solver.atol = 0.0
     with pytest.raises(RuntimeError):
         solver.solve(N)
+
+
+def test_main_cli(tmp_path):
+    """python3 main.py <setup_module> run from source/ (reference source/main.py, notebooks/example.ipynb:61)."""
+    import subprocess
+    src = ROOT / "shakti-fenics_b200" / "source"
+    setup = tmp_path / "setup_cli_case.py"
+    setup.write_text(
+        "import sys\n"
+        f"sys.path.insert(0, {str(ROOT / 'shakti-fenics_b200' / 'setups')!r})\n"
+        "import numpy as np\n"
+        "from _synthetic import md_from_case\n"
+        "from shakti_b200 import configs\n\n"
+        "def initialize(comm):\n"
+        "    case = configs.rect_steady(nx=40, ny=20, nsteps=8)\n"
+        f"    return md_from_case(comm, case, __file__, nt_save=4, results_name={str(tmp_path / 'out')!r})\n")
+    env = dict(**__import__("os").environ, PYTHONPATH=str(tmp_path))
+    r = subprocess.run([sys.executable, "main.py", "setup_cli_case"], cwd=str(src), env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    N = np.load(tmp_path / "out" / "N.npy")
+    assert N.shape == (2, 41 * 21) and np.isfinite(N).all() and np.abs(N[1] - 0.37e6).max() > 1.0
+    # a second run into the same directory must refuse, with exit code 1 (solvers.py:91-102)
+    r2 = subprocess.run([sys.executable, "main.py", "setup_cli_case"], cwd=str(src), env=env, capture_output=True, text=True, timeout=600)
+    assert r2.returncode == 1 and "already exists" in r2.stdout
