@@ -234,8 +234,15 @@ def main():
         t_ms = m.time_kernel(k, reps=20, dt=3600.0)
         by = m.kernel_bytes(k)
         kern[k] = {"ms": t_ms, "algorithmic_GB": by / 1e9, "GBps": by / 1e9 / (t_ms / 1e3), "frac": by / 1e9 / (t_ms / 1e3) / peak}
-    roofline = {"bound": "hbm", "kernel": "spmv_sell_kernel (fine Jacobian, fp64 SELL-32)", "achieved": kern["spmv"]["GBps"],
-                "peak": peak, "unit": "GB/s", "frac": kern["spmv"]["frac"], "traffic": None, "peak_source": peak_src,
+    traffic = None
+    tf = ROOT / "profiles" / "r1_traffic.json"
+    if tf.exists() and world == 1:
+        t_ = json.loads(tf.read_text())["spmv_fine_fp64"]
+        if t_["nside"] == args.nside:
+            traffic = t_["traffic_bytes"]        # dram read+write per launch, ncu --set full (profiles/)
+    roofline = {"bound": "hbm", "kernel": "spmv_sell_kernel<0,double> (fine Jacobian, fp64 SELL-32)", "achieved": kern["spmv"]["GBps"],
+                "peak": peak, "unit": "GB/s", "frac": kern["spmv"]["frac"], "traffic": traffic,
+                "algorithmic_bytes": m.kernel_bytes("spmv"), "peak_source": peak_src,
                 "how": "12*nnz+20*Nv algorithmic bytes / mean of 20 launches, CUDA events on the library stream, matrix >> L2"}
 
     if rank != 0:
