@@ -426,7 +426,16 @@ struct Amg::Impl {
   Reducer red;
   DevBuf<double> scal;
   double* host_scal = nullptr;
-  ~Impl() { if (host_scal) cudaFreeHost(host_scal); }
+  // the V-cycle as a CUDA graph: one launch instead of ~100 kernel launches + ~35 NCCL calls
+  cudaGraphExec_t gexec = nullptr;
+  bool graph_valid = false;    // false after every change of kernel arguments (refresh)
+  bool warm = false;           // one plain cycle after a (re)build so that lazy allocations are done
+  int64_t graph_launches = 0;  // kernels inside the graph (for the launch accounting)
+  void* result_ptr = nullptr;  // where level 0's solution ends up
+  ~Impl() {
+    if (host_scal) cudaFreeHost(host_scal);
+    if (gexec) cudaGraphExecDestroy(gexec);
+  }
 };
 
 Amg::Amg() : p_(new Impl()) {}
@@ -458,6 +467,8 @@ void Amg::setup(const HostCsr& A0, const HostSell& S0, const std::vector<uint8_t
   I.exclude = exclude;
   I.lv.clear();
   I.built = false;
+  I.graph_valid = false;
+  I.warm = false;
   I.red.init(sm_count);
   I.scal.alloc_zero(4, s);
   if (!I.host_scal) SHAKTI_CUDA(cudaMallocHost(&I.host_scal, 4 * sizeof(double)));
@@ -900,6 +911,7 @@ void Amg::refresh_fine_smoother(const DevSell& Afine, const int32_t* fine_diag_p
   Impl& I = *p_;
   cudaStream_t s = I.s;
   if (!I.built || I.lv.empty()) return;
+  I.graph_valid = false;
   AmgLevel& L = *I.lv[0];
   if (L.n > 0) SHAKTI_LAUNCH(amg_dinv_kernel, div_up(L.n, 256), 256, 0, s, L.n, fine_diag_pos, Afine.val.p, L.dinv.p);
   if (I.opt.smoother != 1 || (L.last && I.dense_coarse)) { sync_cycle_precision(I, 0, Afine, false); return; }
@@ -917,7 +929,8 @@ void Amg::refresh_fine_smoother(const DevSell& Afine, const int32_t* fine_diag_p
 void Amg::refresh(const DevSell& Afine, const int32_t* fine_diag_pos) {
   Impl& I = *p_;
   cudaStream_t s = I.s;
-  if (!I.built) build_hierarchy(I, Afine, fine_diag_pos);
+  I.graph_valid = false;
+  if (!I.built) { build_hierarchy(I, Afine, fine_diag_pos); I.warm = false; }
   else
     for (size_t l = 0; l < I.lv.size(); ++l) numeric_level(I, l, Afine, fine_diag_pos);
   update_smoother_bounds(I, Afine);
@@ -1030,18 +1043,66 @@ static void vcycle(Amg::Impl& I, const DevSell& Afine) {
   }
 }
 
+// Runs the V-cycle, through a captured CUDA graph when enabled.  The ping-pong pointers are put
+// back after every cycle, so each cycle (and each capture) uses the same buffers in the same roles
+// and a re-capture after a refresh only updates kernel arguments (cudaGraphExecUpdate).
+template <class T>
+static void run_cycle(Amg::Impl& I, const DevSell& Afine) {
+  cudaStream_t s = I.s;
+  std::vector<std::pair<T*, T*>> saved;
+  for (auto& L : I.lv) saved.push_back({vecs<T>(*L).x.p, vecs<T>(*L).x2.p});
+  auto restore = [&]() {
+    I.result_ptr = vecs<T>(*I.lv[0]).x.p;
+    for (size_t l = 0; l < I.lv.size(); ++l) { vecs<T>(*I.lv[l]).x.p = saved[l].first; vecs<T>(*I.lv[l]).x2.p = saved[l].second; }
+  };
+  if (!I.opt.cuda_graph || !I.warm) {
+    vcycle<T>(I, Afine);
+    restore();
+    I.warm = true;
+    return;
+  }
+  if (!I.graph_valid) {
+    const int64_t before = g_kernel_launches;
+    SHAKTI_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+    cudaGraph_t graph = nullptr;
+    try {
+      vcycle<T>(I, Afine);
+    } catch (...) {
+      cudaStreamEndCapture(s, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      restore();
+      throw;
+    }
+    SHAKTI_CUDA(cudaStreamEndCapture(s, &graph));
+    restore();
+    I.graph_launches = g_kernel_launches - before;
+    g_kernel_launches = before;     // captured, not executed
+    bool updated = false;
+    if (I.gexec) {
+      cudaGraphExecUpdateResultInfo info;
+      updated = cudaGraphExecUpdate(I.gexec, graph, &info) == cudaSuccess;
+      if (!updated) { cudaGetLastError(); cudaGraphExecDestroy(I.gexec); I.gexec = nullptr; }
+    }
+    if (!updated) SHAKTI_CUDA(cudaGraphInstantiate(&I.gexec, graph, 0));
+    SHAKTI_CUDA(cudaGraphDestroy(graph));
+    I.graph_valid = true;
+  }
+  SHAKTI_CUDA(cudaGraphLaunch(I.gexec, s));
+  g_kernel_launches += I.graph_launches;
+}
+
 void Amg::apply(const DevSell& Afine, const double* rin, double* z) {
   Impl& I = *p_;
   cudaStream_t s = I.s;
   AmgLevel& L0 = *I.lv[0];
   if (I.opt.fp32_cycle) {
     launch_d2f(L0.n, rin, L0.vf.b.p, s);
-    vcycle<float>(I, Afine);
-    launch_f2d(L0.n, L0.vf.x.p, z, s);
+    run_cycle<float>(I, Afine);
+    launch_f2d(L0.n, static_cast<const float*>(I.result_ptr), z, s);
   } else {
     if (L0.n) SHAKTI_CUDA(cudaMemcpyAsync(L0.vd.b.p, rin, sizeof(double) * L0.n, cudaMemcpyDeviceToDevice, s));
-    vcycle<double>(I, Afine);
-    if (L0.n) SHAKTI_CUDA(cudaMemcpyAsync(z, L0.vd.x.p, sizeof(double) * L0.n, cudaMemcpyDeviceToDevice, s));
+    run_cycle<double>(I, Afine);
+    if (L0.n) SHAKTI_CUDA(cudaMemcpyAsync(z, I.result_ptr, sizeof(double) * L0.n, cudaMemcpyDeviceToDevice, s));
   }
 }
 

@@ -22,6 +22,7 @@ struct AmgOptions {
   int smoother = 1;             // 0 damped Jacobi (presmooth/postsmooth sweeps), 1 Chebyshev (degree = sweeps)
   double cheby_ratio = 5.0;     // Chebyshev interval [lmax/ratio, lmax] of D^-1 A
   int fp32_cycle = 1;           // 1: V-cycle in single precision (set-up and Krylov stay fp64)
+  int cuda_graph = 1;           // 1: replay the V-cycle as a captured CUDA graph
 };
 
 class Amg {
