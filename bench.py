@@ -41,7 +41,8 @@ def parse():
     ap.add_argument("--linear-rtol", type=float, default=1e-12)
     ap.add_argument("--amg-refresh-every", type=int, default=None, help="override shakti_options.amg_refresh_every")
     ap.add_argument("--no-graph", action="store_true", help="do not replay the AMG V-cycle as a CUDA graph")
-    ap.add_argument("--cpu-sample-nside", type=int, default=400, help="mesh side of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-sample-nside", type=int, default=None,
+                    help="mesh side of the bounded CPU sample (default: sized so that the CPU run takes ~2 minutes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -98,6 +99,15 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def cpu_sample_nside(requested, steps):
+    """Bounded CPU sample: 70-200 us of oracle time per dof and step (measured on the host cores of
+    the GPU box and of the build container), sized for one to three minutes in total."""
+    if requested:
+        return requested
+    dofs = 120.0 / (max(steps, 1) * 1.2e-4)
+    return int(min(500, max(100, dofs ** 0.5)))
+
+
 def cpu_oracle_rate(nside, steps, warmup, target_dofs):
     """Time the CPU oracle (numpy assembly + SuperLU, the stand-in for FEniCSx/PETSc LU) on a
     bounded sample: the same C4 fields on an nside x nside sub-size mesh.  Returns steps/s
@@ -133,13 +143,14 @@ def run_reference(args):
     if rank != 0:
         return
     target = args.nside * args.nside
-    scaled, raw, sample, el = cpu_oracle_rate(args.cpu_sample_nside, args.steps, min(args.warmup, 1), target)
+    nside_cpu = cpu_sample_nside(args.cpu_sample_nside, args.steps + 1)
+    scaled, raw, sample, el = cpu_oracle_rate(nside_cpu, args.steps, min(args.warmup, 1), target)
     line = {
         "impl": "reference", "metric": METRIC, "value": scaled, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": min(args.warmup, 1), "ms_per_step": 1e3 / scaled, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"C4 synthetic ice-sheet margin mesh {args.nside}x{args.nside} vertices ({target} dofs), "
-                               "turbulent K(b,Re), dt=3600 s", "sample_nside": args.cpu_sample_nside},
+                               "turbulent K(b,Re), dt=3600 s", "sample_nside": nside_cpu},
         "cpu_baseline": {"value": scaled, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
                          "raw_steps_per_sec_on_sample": raw},
         "e2e": {"value": scaled, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -252,7 +263,7 @@ def main():
         return
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
-        scaled, raw, sample, _ = cpu_oracle_rate(args.cpu_sample_nside, 2, 1, nv)
+        scaled, raw, sample, _ = cpu_oracle_rate(cpu_sample_nside(args.cpu_sample_nside, 5), 2, 1, nv)
         cpu_baseline = {"value": scaled, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
                         "raw_steps_per_sec_on_sample": raw}
     n_newton = st1["newton_its"] - st0["newton_its"]
