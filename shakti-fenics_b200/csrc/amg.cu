@@ -167,6 +167,52 @@ amg_spgemm_kernel(SellView A, const int32_t* __restrict__ Alen, SellView B, cons
   }
 }
 
+// Same product with one WARP per row, for the small levels where one thread per row leaves the GPU
+// idle and the rows of R are long: each lane owns output positions of C's row (lane, lane+32, ...)
+// and accumulates its entries itself -> no atomics, same summation order every run.
+__global__ void __launch_bounds__(128)
+amg_spgemm_warp_kernel(SellView A, const int32_t* __restrict__ Alen, SellView B, const int32_t* __restrict__ Blen,
+                       int32_t Bn_rows, const int32_t* __restrict__ Cslice, const int32_t* __restrict__ Ccol,
+                       const int32_t* __restrict__ Clen, double* __restrict__ Cval) {
+  const int32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= A.n_rows) return;
+  const int32_t abase = A.slice_ptr[row >> 5] + (row & 31);
+  const int32_t cbase = Cslice[row >> 5] + (row & 31);
+  const int32_t clen = Clen[row], alen = Alen[row];
+  for (int pos = lane; pos < clen; pos += 32) {
+    const int32_t c = Ccol[cbase + 32 * pos];
+    double acc = 0.0;
+    for (int ka = 0; ka < alen; ++ka) {
+      const int32_t j = A.col[abase + 32 * ka];
+      if (j >= Bn_rows) continue;
+      const double a = A.val[abase + 32 * ka];
+      if (a == 0.0) continue;
+      const int32_t bbase = B.slice_ptr[j >> 5] + (j & 31);
+      int lo = 0, hi = Blen[j] - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (B.col[bbase + 32 * mid] < c) lo = mid + 1; else hi = mid;
+      }
+      if (hi >= 0 && lo == hi && B.col[bbase + 32 * lo] == c) acc += a * B.val[bbase + 32 * lo];
+    }
+    Cval[cbase + 32 * pos] = acc;
+  }
+}
+
+// C = A B numerically (pattern of C known), thread-per-row for large matrices, warp-per-row for small ones
+static void spgemm_numeric(const DevSell& A, const DevSell& B, DevSell& C, cudaStream_t s) {
+  if (A.n_rows == 0) return;
+  if (A.n_rows <= 400000) {
+    SHAKTI_LAUNCH(amg_spgemm_warp_kernel, div_up((int64_t)A.n_rows * 32, 128), 128, 0, s, view(A), A.rowlen.p, view(B), B.rowlen.p,
+                  B.n_rows, C.slice_ptr.p, C.col.p, C.rowlen.p, C.val.p);
+  } else {
+    SHAKTI_CUDA(cudaMemsetAsync(C.val.p, 0, sizeof(double) * C.padded, s));
+    SHAKTI_LAUNCH(amg_spgemm_kernel, div_up(A.n_rows, 128), 128, 0, s, view(A), A.rowlen.p, view(B), B.rowlen.p, B.n_rows,
+                  C.slice_ptr.p, C.col.p, C.rowlen.p, C.val.p);
+  }
+}
+
 // dense coarse operator: D[i*ld + j] (ld = 2n), right half = identity
 __global__ void amg_dense_fill_kernel(SellView A, const int32_t* __restrict__ Alen, int32_t n, double* __restrict__ D) {
   const int32_t row = blockIdx.x * blockDim.x + threadIdx.x;
@@ -517,15 +563,8 @@ static void numeric_level(Amg::Impl& I, size_t l, const DevSell& Afine, const in
   if (L.R.padded)
     SHAKTI_LAUNCH(amg_gather_vals_kernel, (int)std::min<int64_t>(148 * 8, std::max<int64_t>(1, (L.R.padded + 255) / 256)), 256, 0, s,
                   L.R.padded, L.tmap.p, L.P.val.p, L.R.val.p);
-  SHAKTI_CUDA(cudaMemsetAsync(L.AP.val.p, 0, sizeof(double) * L.AP.padded, s));
-  if (L.n > 0)
-    SHAKTI_LAUNCH(amg_spgemm_kernel, div_up(L.n, 128), 128, 0, s, view(A), A.rowlen.p, view(L.P), L.P.rowlen.p, L.P.n_rows,
-                  L.AP.slice_ptr.p, L.AP.col.p, L.AP.rowlen.p, L.AP.val.p);
-  DevSell& Ac = I.lv[l + 1]->A;
-  SHAKTI_CUDA(cudaMemsetAsync(Ac.val.p, 0, sizeof(double) * Ac.padded, s));
-  if (L.R.n_rows > 0)
-    SHAKTI_LAUNCH(amg_spgemm_kernel, div_up(L.R.n_rows, 128), 128, 0, s, view(L.R), L.R.rowlen.p, view(L.AP), L.AP.rowlen.p,
-                  L.AP.n_rows, Ac.slice_ptr.p, Ac.col.p, Ac.rowlen.p, Ac.val.p);
+  spgemm_numeric(A, L.P, L.AP, s);                 // A restricted to the columns P has rows for
+  spgemm_numeric(L.R, L.AP, I.lv[l + 1]->A, s);    // Galerkin: R (A P)
 }
 
 // Copies the V-cycle reads: smoother diagonal in the cycle's precision and, for the mixed-precision
