@@ -55,3 +55,30 @@ def make_model(xy, cells, f, bc, N_bdry, **opt):
 
 def relinf(a, b):
     return float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(np.max(np.abs(b)), 1e-300))
+
+
+class OracleStepper:
+    """Adapter of the CPU oracle for shakti_b200.golden.check."""
+
+    def __init__(self, dump, **kw):
+        from oracle.shakti_oracle import Params
+        from shakti_b200.golden import FIELDS
+        o = ShaktiOracle(dump.xy, dump.cells, params=Params(**dump.meta["params"]), quad=dump.quad, **kw)
+        for k in FIELDS:
+            getattr(o, k)[:] = dump.initial[k]
+        o.q[:] = dump.initial["q"]
+        o.set_dirichlet(dump.bc_dofs, dump.N_bdry)
+        o.start()
+        self.o = o
+
+    def assemble(self, dt):
+        F, v = self.o.assemble(dt)
+        return F, (self.o.rowptr, self.o.col, v)
+
+    def step(self, dt):
+        return self.o.step(dt)[0]
+
+    def state(self):
+        return dict(N=self.o.N, b=self.o.b, q=self.o.q, melt_n=self.o.melt_n)
+
+

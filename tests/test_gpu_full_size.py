@@ -108,3 +108,18 @@ def test_large_step_is_reproducible():
         out.append((m.get_field("N"), m.get_field("b")))
         m.close()
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+
+
+def test_model_against_golden_dump(tmp_path):
+    """The checker a real FEniCSx dump would be run through (here: a dump written by the oracle)."""
+    from common import make_case, make_oracle
+    from shakti_b200 import golden
+    c = make_case(nx=16, ny=12, seed=13)
+    golden.write_dump(tmp_path / "dump", make_oracle(*c), [360.0, 3600.0, 3600.0])
+    d = golden.Dump(tmp_path / "dump")
+    s = golden.ModelStepper(d)
+    try:
+        rep = golden.check(d, s, pattern=s.m.csr())
+        assert rep["pattern_equal"] and all(rep[f"step{i}"]["niter"][0] == rep[f"step{i}"]["niter"][1] for i in range(3))
+    finally:
+        s.m.close()

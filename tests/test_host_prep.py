@@ -146,3 +146,24 @@ def test_invalid_mesh_is_rejected():
     xy = np.zeros((3, 2))
     with pytest.raises(capi.ShaktiError):
         capi.HostMesh(xy, np.array([[0, 1, 5]], dtype=np.int32))
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under the product package may import it."""
+    import ast
+    pkg = ROOT / "shakti-fenics_b200"
+    bad = []
+    for f in list(pkg.rglob("*.py")):
+        tree = ast.parse(f.read_text())
+        for node in ast.walk(tree):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom) and node.module:
+                names = [node.module]
+            if any(n == "oracle" or n.startswith("oracle.") for n in names):
+                bad.append(str(f))
+    assert not bad, bad
+    for f in (pkg / "csrc").glob("*"):
+        if f.suffix in (".cu", ".cpp", ".h"):
+            assert "oracle" not in f.read_text().lower(), f
