@@ -134,6 +134,26 @@ class B200NewtonSolver:
             else:
                 self.model.get_field(k, out=getattr(self, k).x.array)
 
+    def set_inputs(self, values):
+        """Replace the water-input field md.inputs on the device (time-dependent forcing, an
+        extension: the reference's inputs are static, model_setup.py:47)."""
+        self.model.set_field("inputs", values)
+
+    STATE = ("N", "N_n", "b", "melt_n")
+
+    def checkpoint(self, path, step):
+        """Write the full device state (extension: the reference can only be restarted from scratch)."""
+        m = self.model
+        np.savez(path, step=step, q=m.get_flux(), **{k: m.get_field(k) for k in self.STATE})
+
+    def restore(self, path):
+        """Load a state written by ``checkpoint``; returns the index of the last completed step."""
+        d = np.load(path)
+        for k in self.STATE:
+            self.model.set_field(k, d[k])
+        self.model.set_flux(d["q"])
+        return int(d["step"])
+
     def fields_for_output(self):
         """b, N, qx, qy in the caller's vertex numbering; on several GPUs every rank returns
         its owned entries and zeros elsewhere (summed by the caller)."""
@@ -177,7 +197,7 @@ def solve(md):
     md.comm.barrier()
     if md.rank == 0:
         try:
-            os.makedirs(md.results_name, exist_ok=False)
+            os.makedirs(md.results_name, exist_ok=bool(getattr(md, "resume", False)))
         except FileExistsError:
             print(f"Error: Directory '{md.results_name}' already exists.\n"
                   "Choose another name in setup file or delete this directory.")
@@ -234,7 +254,22 @@ def solve(md):
     solver.sync_host = False            # state stays on the device between saves
     md.solver = solver
 
-    for i in range(nt):
+    # extensions (off unless the setup sets them): md.inputs_of_t(t) -> nodal array for time-dependent
+    # forcing, md.resume = True to continue from <results>/checkpoint.npz written every nt_check saves
+    inputs_of_t = getattr(md, "inputs_of_t", None)
+    first = 0
+    ckpt = os.path.join(md.results_name, "checkpoint.npz")
+    if getattr(md, "resume", False) and os.path.exists(ckpt):
+        first = solver.restore(ckpt) + 1
+        if md.rank == 0:
+            for name, arr in (("b", b_arr), ("N", N_arr), ("qx", qx_arr), ("qy", qy_arr)):
+                old = os.path.join(md.results_name, name + ".npy")
+                if os.path.exists(old):
+                    prev = np.load(old)
+                    arr[:min(arr.shape[0], prev.shape[0])] = prev[:arr.shape[0]]
+            j = len(range(0, first, md.nt_save))
+
+    for i in range(first, nt):
 
         if md.rank == 0 and (i + 1) % 10 == 0:
             print(f"Time step {i+1} of {nt} completed ({(i+1)/nt*100:.1f}%)", end='\r')
@@ -243,6 +278,9 @@ def solve(md):
         if i > 0:
             dt_ = np.abs(md.timesteps[i] - md.timesteps[i - 1])
             dt.value = dt_
+
+        if inputs_of_t is not None:
+            solver.set_inputs(inputs_of_t(md.timesteps[i]))
 
         # effective pressure
         niter, converged = solver.solve(N)
@@ -267,6 +305,10 @@ def solve(md):
                     np.save(md.results_name + '/qy.npy', qy_arr)
 
                 j += 1
+
+            if i % md.nt_check == 0 and getattr(md, "resume", False) and md.size == 1:
+                solver.copy_N_to_N_n()          # the checkpoint holds the state the next step starts from
+                solver.checkpoint(ckpt, i)
 
         # previous-step solution
         solver.copy_N_to_N_n()

@@ -122,3 +122,39 @@ def test_main_cli(tmp_path):
     # a second run into the same directory must refuse, with exit code 1 (solvers.py:91-102)
     r2 = subprocess.run([sys.executable, "main.py", "setup_cli_case"], cwd=str(src), env=env, capture_output=True, text=True, timeout=600)
     assert r2.returncode == 1 and "already exists" in r2.stdout
+
+
+def test_time_dependent_inputs_and_resume(tmp_path):
+    """Extensions of SURVEY §8(f)4: md.inputs_of_t and checkpoint/resume give the same fields as one straight run."""
+    import solvers
+    from _synthetic import md_from_case
+    from shakti_b200 import configs, fem
+
+    def make(results, nsteps):
+        case = configs.lakes_fill_drain(nside=40, nsteps=13)
+        case.meta["t_pulse"], case.meta["tau"] = 5 * 3600.0, 3 * 3600.0
+        md = md_from_case(fem.comm_world(), case, str(ROOT / "shakti-fenics_b200" / "setups" / "setup_lakes64m.py"), nt_save=2,
+                          nt_check=2, results_name=str(results))
+        md.timesteps = case.timesteps[:nsteps]
+        md.inputs_of_t = lambda t: configs.lake_pulse_inputs(case, t)
+        return md, case
+
+    md, case = make(tmp_path / "straight", 12)
+    solvers.solve(md)
+    N_ref, b_ref = np.load(tmp_path / "straight" / "N.npy"), np.load(tmp_path / "straight" / "b.npy")
+    assert np.abs(N_ref[-1] - N_ref[0]).max() > 0
+    # forcing really is time dependent: a run with static inputs differs
+    md0, _ = make(tmp_path / "static", 12)
+    md0.inputs_of_t = None
+    solvers.solve(md0)
+    assert np.abs(np.load(tmp_path / "static" / "N.npy")[-1] - N_ref[-1]).max() > 1e-8 * np.abs(N_ref[-1]).max()
+    # stop after 8 steps (last checkpoint after step index 6), resume to 12
+    md1, _ = make(tmp_path / "resumed", 8)
+    md1.resume = True
+    solvers.solve(md1)
+    md2, _ = make(tmp_path / "resumed", 12)
+    md2.resume = True
+    solvers.solve(md2)
+    N2, b2 = np.load(tmp_path / "resumed" / "N.npy"), np.load(tmp_path / "resumed" / "b.npy")
+    assert N2.shape == N_ref.shape
+    assert relinf(N2[-1], N_ref[-1]) < 1e-8 and relinf(b2[-1], b_ref[-1]) < 1e-8
