@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--precond", default="amg")
     ap.add_argument("--linear-rtol", type=float, default=1e-12)
     ap.add_argument("--amg-refresh-every", type=int, default=None, help="override shakti_options.amg_refresh_every")
+    ap.add_argument("--lagged-smoother-halo", action="store_true", help="multi-GPU: amg_smoother_halo = 0")
     ap.add_argument("--no-graph", action="store_true", help="do not replay the AMG V-cycle as a CUDA graph")
     ap.add_argument("--cpu-sample-nside", type=int, default=None,
                     help="mesh side of the bounded CPU sample (default: sized so that the CPU run takes ~2 minutes)")
@@ -192,6 +193,8 @@ def main():
     extra = {} if args.amg_refresh_every is None else {"amg_refresh_every": args.amg_refresh_every}
     if args.no_graph:
         extra["amg_cuda_graph"] = 0
+    if args.lagged_smoother_halo:
+        extra["amg_smoother_halo"] = 0
     m = capi.Model(case.xy, case.cells, device=local_rank, precond=args.precond, linear_rtol=args.linear_rtol, **extra)
     configs.apply_case(m, case)
     dts = case.dts()

@@ -97,7 +97,8 @@ typedef struct shakti_options {
   int32_t amg_smoother;         /* 0 = damped Jacobi, 1 = Chebyshev */
   int32_t amg_fp32_cycle;       /* 1 = V-cycle in single precision under FGMRES (set-up, Krylov, residuals stay fp64) */
   int32_t amg_cuda_graph;       /* 1 = on a single GPU the V-cycle is replayed as a captured CUDA graph */
-  int32_t reserved0;
+  int32_t amg_smoother_halo;    /* multi-GPU: 1 = exchange ghosts before every smoothing step, 0 = only before the residual and the
+                                   prolongation (ghosts lag inside the smoother: fewer messages, a slightly weaker preconditioner) */
   double b_min;                 /* md.b_min, model_setup.py:53 */
   int32_t assembly_kernel;      /* 0 = row-block staged gather (default), 1 = element atomics */
   int32_t reorder;              /* 1 = internal Morton reordering (default), 0 = keep caller order */

@@ -23,6 +23,8 @@ struct AmgOptions {
   double cheby_ratio = 5.0;     // Chebyshev interval [lmax/ratio, lmax] of D^-1 A
   int fp32_cycle = 1;           // 1: V-cycle in single precision (set-up and Krylov stay fp64)
   int cuda_graph = 1;           // 1: replay the V-cycle as a captured CUDA graph
+  int smoother_halo = 1;        // 1: halo exchange before every smoothing step; 0: only before residual / prolongation
+                                //    (ghost values lag one step inside the smoother: hybrid smoothing, fewer messages)
 };
 
 class Amg {

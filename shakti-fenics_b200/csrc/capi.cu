@@ -19,24 +19,6 @@ void set_last_error(const std::string& msg) { t_last_error = msg; }
 // default degree-7 table: collapsed Gauss-Jacobi 4x4 (stand-in for Basix' default; see
 // shakti_b200/quadrature.py which generates these digits and tests/test_quadrature.py)
 static void default_k_rule(std::vector<double>& pts, std::vector<double>& wts);
-// Radon's 7-point degree-5 rule
-static void radon7(std::vector<double>& pts, std::vector<double>& wts) {
-  const double s15 = std::sqrt(15.0);
-  const double a[2] = {(6.0 - s15) / 21.0, (6.0 + s15) / 21.0};
-  const double w[2] = {(155.0 - s15) / 1200.0, (155.0 + s15) / 1200.0};
-  pts = {1.0 / 3.0, 1.0 / 3.0};
-  wts = {0.5 * 9.0 / 40.0};
-  for (int k = 0; k < 2; ++k) {
-    const double c = 1.0 - 2.0 * a[k];
-    const double l[3][3] = {{c, a[k], a[k]}, {a[k], c, a[k]}, {a[k], a[k], c}};
-    for (int i = 0; i < 3; ++i) {
-      pts.push_back(l[i][1]);
-      pts.push_back(l[i][2]);
-      wts.push_back(0.5 * w[k]);
-    }
-  }
-}
-
 }  // namespace shakti
 
 using namespace shakti;
@@ -172,7 +154,18 @@ static double norm2(shakti_model* m, const double* v) {
   return std::sqrt(std::max(m->host_scal[0], 0.0));
 }
 
+// The quadrature tables live in __constant__ memory, which is shared by all models of the process:
+// a model re-uploads its own tables whenever another model used the kernels last.
+static const shakti_model* g_rule_owner = nullptr;
+static void ensure_rules(shakti_model* m) {
+  if (g_rule_owner == m) return;
+  upload_k_rule((int)m->kq_wts.size(), m->kq_pts.data(), m->kq_wts.data(), m->stream);
+  if (!m->dprm.n_is_3) upload_reaction_rule((int)m->kq_wts.size(), m->kq_pts.data(), m->kq_wts.data(), m->stream);
+  g_rule_owner = m;
+}
+
 static void compute_kbar(shakti_model* m) {
+  ensure_rules(m);
   launch_kbar(m->hm.ne, m->c0.p, m->c1.p, m->c2.p, m->x.p, m->y.p, m->b.p, m->qx.p, m->qy.p, m->kbar.p,
               m->dprm, m->stream);
 }
@@ -180,6 +173,7 @@ static void compute_kbar(shakti_model* m) {
 // residual (+ Jacobian) at the current state; Kbar must be current
 static void assemble(shakti_model* m, double dt, int want_J) {
   refresh_h0(m);
+  ensure_rules(m);
   const int32_t no = m->hm.n_owned;
   if (m->opt.assembly_kernel == 0 && m->ab.ok) {
     AssemblyPlanView pl{no, m->ab.rows_per_block, m->ab.n_blocks, m->ab.max_cells, m->ab.max_verts, m->ab_eptr.p,
@@ -210,6 +204,7 @@ static void ensure_amg(shakti_model* m) {
   ao.cheby_ratio = m->opt.amg_cheby_ratio;
   ao.smoother = m->opt.amg_smoother;
   ao.fp32_cycle = m->opt.amg_fp32_cycle;
+  ao.smoother_halo = m->opt.amg_smoother_halo;
   // measured on 8 B200s: replaying NCCL exchanges from a graph is slower than issuing them (84 vs 70 ms/step),
   // on one GPU the graph saves ~3 %: so the graph is used on a single rank only
   ao.cuda_graph = m->opt.amg_cuda_graph && !comm().active();
@@ -468,12 +463,8 @@ static void create(int64_t nv, int64_t ne, const double* xy, const int32_t* cell
   m->gmres.init(hm.n_owned, hm.n_local, std::max(2, m->opt.gmres_restart), m->sm_count, m->stream);
   // quadrature tables
   default_k_rule(m->kq_pts, m->kq_wts);
-  upload_k_rule((int)m->kq_wts.size(), m->kq_pts.data(), m->kq_wts.data(), m->stream);
-  {
-    std::vector<double> p, w;
-    if (m->dprm.n_is_3) radon7(p, w); else { p = m->kq_pts; w = m->kq_wts; }
-    upload_reaction_rule((int)w.size(), p.data(), w.data(), m->stream);
-  }
+  g_rule_owner = nullptr;
+  ensure_rules(m.get());
   // stats
   m->st.n_vert = nv; m->st.n_cell = ne;
   m->st.n_owned = hm.n_owned; m->st.n_local = hm.n_local; m->st.n_cell_local = hm.ne; m->st.nnz_local = hm.A.nnz();
@@ -484,6 +475,7 @@ static void create(int64_t nv, int64_t ne, const double* xy, const int32_t* cell
 
 static void destroy(shakti_model* m) {
   if (!m) return;
+  if (g_rule_owner == m) g_rule_owner = nullptr;
   cudaSetDevice(m->device);
   if (m->stream) cudaStreamSynchronize(m->stream);
   // swap-safe: DevBuf destructors free whatever pointer they currently hold
@@ -609,7 +601,7 @@ int shakti_default_options(shakti_options* o) {
   o->linear_rtol = 1e-12; o->linear_atol = 0.0; o->linear_max_it = 2000; o->gmres_restart = 40;
   o->amg_refresh_every = 1; o->amg_max_levels = 12; o->amg_coarse_size = 128; o->amg_presmooth = 2; o->amg_postsmooth = 2;
   o->amg_smoother_omega = 0.67; o->amg_prolong_omega = 0.67; o->amg_strength_theta = 0.08; o->amg_cheby_ratio = 5.0;
-  o->amg_smoother = 1; o->amg_fp32_cycle = 1; o->amg_cuda_graph = 1; o->reserved0 = 0;
+  o->amg_smoother = 1; o->amg_fp32_cycle = 1; o->amg_cuda_graph = 1; o->amg_smoother_halo = 1;
   o->b_min = 1.0e-5; o->assembly_kernel = 0; o->reorder = 1;
   return SHAKTI_OK;
 }
@@ -702,8 +694,8 @@ int shakti_set_quadrature(shakti_model* m, int32_t n_pts, const double* pts_xy, 
   use_device(m);
   m->kq_pts.assign(pts_xy, pts_xy + 2 * n_pts);
   m->kq_wts.assign(wts, wts + n_pts);
-  upload_k_rule(n_pts, pts_xy, wts, m->stream);
-  if (!m->dprm.n_is_3) upload_reaction_rule(n_pts, pts_xy, wts, m->stream);
+  g_rule_owner = nullptr;
+  ensure_rules(m);
   SHAKTI_CATCH
 }
 
@@ -717,7 +709,8 @@ int shakti_set_options(shakti_model* m, const shakti_options* opt) {
                            opt->amg_prolong_omega != m->opt.amg_prolong_omega ||
                            opt->amg_strength_theta != m->opt.amg_strength_theta ||
                            opt->amg_cheby_ratio != m->opt.amg_cheby_ratio || opt->amg_smoother != m->opt.amg_smoother ||
-                           opt->amg_fp32_cycle != m->opt.amg_fp32_cycle || opt->amg_cuda_graph != m->opt.amg_cuda_graph;
+                           opt->amg_fp32_cycle != m->opt.amg_fp32_cycle || opt->amg_cuda_graph != m->opt.amg_cuda_graph ||
+                           opt->amg_smoother_halo != m->opt.amg_smoother_halo;
   SHAKTI_REQUIRE(opt->reorder == m->opt.reorder, "reorder can only be chosen at create time");
   const int restart_old = m->opt.gmres_restart;
   m->opt = *opt;

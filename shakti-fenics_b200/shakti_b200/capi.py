@@ -47,7 +47,7 @@ class Options(C.Structure):
         ("amg_smoother_omega", C.c_double), ("amg_prolong_omega", C.c_double),
         ("amg_strength_theta", C.c_double), ("amg_cheby_ratio", C.c_double),
         ("amg_smoother", C.c_int32), ("amg_fp32_cycle", C.c_int32),
-        ("amg_cuda_graph", C.c_int32), ("reserved0", C.c_int32),
+        ("amg_cuda_graph", C.c_int32), ("amg_smoother_halo", C.c_int32),
         ("b_min", C.c_double), ("assembly_kernel", C.c_int32), ("reorder", C.c_int32),
     ]
 

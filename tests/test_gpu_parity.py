@@ -209,3 +209,21 @@ def test_assembly_kernel_variants(kernel):
             assert np.array_equal(F, F2) and np.array_equal(J, J2)
     finally:
         m.close()
+
+
+def test_two_models_with_different_quadrature_tables():
+    """The tables live in __constant__ memory shared by the process: models must not disturb each other."""
+    from oracle import quadrature
+    c = make_case(seed=14)
+    o1 = make_oracle(*c)
+    pts, wts = quadrature.gauss_jacobi_triangle(12)
+    o2 = make_oracle(*c, quad=(pts, wts))
+    m1, m2 = make_model(*c), make_model(*c)
+    try:
+        m2.set_quadrature(pts, wts)
+        for _ in range(2):
+            assert relinf(m1.kbar(), o1.kbar()) < 1e-13
+            assert relinf(m2.kbar(), o2.kbar()) < 1e-13
+        assert relinf(o1.kbar(), o2.kbar()) > 1e-9          # the two tables really differ on this case
+    finally:
+        m1.close(); m2.close()
