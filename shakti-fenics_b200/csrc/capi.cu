@@ -63,7 +63,6 @@ struct shakti_model {
   Reducer red;
   std::unique_ptr<Amg> amg;
   bool amg_setup_done = false;
-  int64_t solves_since_refresh = 0;
   int64_t step_of_refresh = -1000000;  // st.steps at the last AMG refresh
   int newton_it_in_step = 0;           // Newton iteration index of the solve in progress
   int its_after_refresh = 0;           // Krylov iterations of the first solve after the last refresh
@@ -213,7 +212,6 @@ static void ensure_amg(shakti_model* m) {
   m->amg.reset(new Amg());
   m->amg->setup(m->hm.A, m->hm.S, excl, m->hm.nbrs, &m->halo, ao, m->sm_count, m->stream);
   m->amg_setup_done = true;
-  m->solves_since_refresh = 0;
 }
 
 // Solve J dx = rhs (rhs, dx owned-length device vectors) with the configured method.

@@ -117,9 +117,6 @@ void launch_multi_axpy_neg_scale(int64_t n, int nvec, const double* V, int64_t l
 // y = sum_k h[k] V_k
 void launch_combine(int64_t n, int nvec, const double* V, int64_t ld, const double* h, double* y,
                     cudaStream_t s);
-// y = alpha_dev[0] * x (alpha read from device), optional reciprocal
-void launch_scale_dev(int64_t n, const double* x, const double* alpha_dev, int reciprocal, double* y,
-                      cudaStream_t s);
 void launch_axpy(int64_t n, double alpha, const double* x, double* y, cudaStream_t s);  // y += alpha x
 void launch_xmy_masked(int64_t n, const double* a, const uint8_t* mask, double* out, cudaStream_t s);
 void launch_pointwise_mul(int64_t n, const double* a, const double* b, double scale, double* out, cudaStream_t s);

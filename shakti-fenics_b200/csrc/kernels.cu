@@ -908,17 +908,6 @@ void launch_combine(int64_t n, int nvec, const double* V, int64_t ld, const doub
 }
 
 // ------------------------------------------------------------------ streaming vector kernels
-// (x, y without __restrict__: called in place)
-__global__ void scale_dev_kernel(int64_t n, const double* x, const double* __restrict__ alpha, int reciprocal,
-                                 double* y) {
-  const double a = reciprocal ? 1.0 / alpha[0] : alpha[0];
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = a * x[i];
-}
-void launch_scale_dev(int64_t n, const double* x, const double* alpha_dev, int reciprocal, double* y, cudaStream_t s) {
-  if (n == 0) return;
-  SHAKTI_LAUNCH(scale_dev_kernel, stream_blocks(n), 256, 0, s, n, x, alpha_dev, reciprocal, y);
-}
 __global__ void axpy_kernel(int64_t n, double alpha, const double* __restrict__ x, double* __restrict__ y) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] += alpha * x[i];

@@ -5,55 +5,7 @@
 
 namespace shakti {
 
-// ------------------------------------------------------------------ small device-side state
-__global__ void gmres_begin_kernel(int m, double* g, double* scal) {
-  // scal[0] = <r,r> on entry
-  const double beta = sqrt(fmax(scal[0], 0.0));
-  for (int i = 0; i <= m; ++i) g[i] = 0.0;
-  g[0] = beta;
-  scal[1] = beta;
-}
-
-// Column j of the Hessenberg matrix: combine the two Gram-Schmidt passes, take the norm of the
-// new direction from <w,w> of pass two (Pythagoras on the tiny second correction), apply the
-// stored Givens rotations, create the new one, update the residual estimate.
-__global__ void gmres_update_kernel(int j, int m, const double* h, const double* h2, double* H, double* cs,
-                                    double* sn, double* g, double* scal) {
-  double* col = H + (size_t)j * (m + 1);
-  double corr = 0.0;
-  for (int i = 0; i <= j; ++i) {
-    col[i] = h[i] + h2[i];
-    corr += h2[i] * h2[i];
-  }
-  const double ww = h2[j + 1];
-  const double hj1 = sqrt(fmax(ww - corr, 0.0));
-  col[j + 1] = hj1;
-  for (int i = 0; i < j; ++i) {
-    const double t = cs[i] * col[i] + sn[i] * col[i + 1];
-    col[i + 1] = -sn[i] * col[i] + cs[i] * col[i + 1];
-    col[i] = t;
-  }
-  const double d = hypot(col[j], col[j + 1]);
-  const double c = d > 0 ? col[j] / d : 1.0, s = d > 0 ? col[j + 1] / d : 0.0;
-  cs[j] = c;
-  sn[j] = s;
-  col[j] = d;
-  col[j + 1] = 0.0;
-  g[j + 1] = -s * g[j];
-  g[j] = c * g[j];
-  scal[2] = hj1;
-  scal[3] = fabs(g[j + 1]);
-}
-
-__global__ void gmres_solve_y_kernel(int k, int m, const double* H, const double* g, double* y) {
-  for (int i = k - 1; i >= 0; --i) {
-    double s = g[i];
-    for (int l = i + 1; l < k; ++l) s -= H[(size_t)l * (m + 1) + i] * y[l];
-    const double d = H[(size_t)i * (m + 1) + i];
-    y[i] = d != 0.0 ? s / d : 0.0;
-  }
-}
-
+// ------------------------------------------------------------------ small helpers
 __global__ void sub_kernel(int64_t n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = a[i] - b[i];
@@ -82,15 +34,11 @@ void Gmres::init(int64_t n_owned, int64_t n_local, int restart, int sm_count, cu
   z_.alloc_zero(std::max<int64_t>(n_local, 1), s);
   u_.alloc_zero(ld_, s);
   r_.alloc_zero(ld_, s);
-  const size_t ns = (size_t)(m_ + 2) * 2 + (size_t)(m_ + 1) * m_ + 2 * m_ + (m_ + 1) + m_ + 4;
-  small_.alloc_zero(ns, s);
+  // device scalars: h[m+2] and h2[m+2] (adjacent: read back together), y[m], scal[4]
+  small_.alloc_zero((size_t)(m_ + 2) * 2 + m_ + 4, s);
   double* p = small_.p;
   h_ = p; p += m_ + 2;
   h2_ = p; p += m_ + 2;
-  H_ = p; p += (size_t)(m_ + 1) * m_;
-  cs_ = p; p += m_;
-  sn_ = p; p += m_;
-  g_ = p; p += m_ + 1;
   y_ = p; p += m_;
   scal_ = p;
   red_.init(sm_count);

@@ -35,9 +35,8 @@ class Gmres {
   cudaStream_t s_ = 0;
   DevBuf<double> V_, Z_, z_, u_, r_, small_;
   Reducer red_;
-  double* host_status_ = nullptr;  // pinned: [0] = residual estimate, [1] = beta
-  // layout of small_: h[m+2] h2[m+2] H[(m+1)*m] cs[m] sn[m] g[m+1] y[m] scal[4]
-  double *h_, *h2_, *H_, *cs_, *sn_, *g_, *y_, *scal_;
+  double* host_status_ = nullptr;  // pinned staging of the Gram-Schmidt coefficients / y
+  double *h_, *h2_, *y_, *scal_;   // device scalars inside small_ (Hessenberg algebra runs on the host)
  public:
   ~Gmres();
 };

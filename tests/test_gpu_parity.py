@@ -227,3 +227,23 @@ def test_two_models_with_different_quadrature_tables():
         assert relinf(o1.kbar(), o2.kbar()) > 1e-9          # the two tables really differ on this case
     finally:
         m1.close(); m2.close()
+
+
+def test_step_host_matches_step_and_get_field():
+    """shakti_step_host = set inputs (host) + step + read b, N, qx, qy back into host buffers."""
+    import torch
+    c = make_case(seed=15)
+    m1, m2 = make_model(*c), make_model(*c)
+    try:
+        nv = c[0].shape[0]
+        inputs = torch.from_numpy(c[2]["inputs"] * 1.5).clone().pin_memory()
+        outs = [torch.empty(nv, dtype=torch.float64).pin_memory() for _ in range(4)]
+        it2, cv2 = m2.step_host(DT, inputs.data_ptr(), *[o.data_ptr() for o in outs])
+        m1.set_field("inputs", inputs.numpy())
+        it1, cv1 = m1.step(DT)
+        assert (it1, cv1) == (it2, cv2)
+        q = m1.get_flux()
+        for got, ref in zip(outs, (m1.get_field("b"), m1.get_field("N"), q[:, 0], q[:, 1])):
+            assert np.array_equal(got.numpy(), ref)
+    finally:
+        m1.close(); m2.close()
