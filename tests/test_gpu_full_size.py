@@ -123,3 +123,17 @@ def test_model_against_golden_dump(tmp_path):
         assert rep["pattern_equal"] and all(rep[f"step{i}"]["niter"][0] == rep[f"step{i}"]["niter"][1] for i in range(3))
     finally:
         s.m.close()
+
+
+def test_model_against_committed_golden_dump():
+    """The CUDA path against the committed fixture tests/golden/small_dump."""
+    from pathlib import Path
+    from shakti_b200 import golden
+    d = golden.Dump(Path(__file__).parent / "golden" / "small_dump")
+    s = golden.ModelStepper(d)
+    try:
+        rep = golden.check(d, s, pattern=s.m.csr())
+        assert rep["pattern_equal"]
+        assert all(rep[f"step{i}"]["niter"][0] == rep[f"step{i}"]["niter"][1] for i in range(len(d.steps)))
+    finally:
+        s.m.close()
