@@ -406,13 +406,30 @@ assemble_blocks_kernel(int32_t n_owned, int32_t rows_per_block, int32_t cap, int
       for (int b = 0; b < 3; ++b) sK[(3 + 3 * a + b) * cap + le] = (bc[a] || bc[b]) ? 0.0 : o.J[a][b];
     }
   }
-  __syncthreads();
-  // ---- phase 2
-  if ((int32_t)threadIdx.x >= nrows) return;
+  // ---- phase 2 (its first loads are issued before the barrier so that they are in flight while
+  // the block's last cells finish: the gather codes of the row's first kPre entries and the bounds
+  // of its incident-cell list)
+  constexpr int kPre = 8;
+  const bool has_row = (int32_t)threadIdx.x < nrows;
   const int32_t row = r0 + threadIdx.x;
+  int32_t base = 0, w = 0, ib = 0, ie = 0;
+  uint32_t pre[kPre];
+  if (has_row) {
+    const int32_t slice = row >> 5;
+    base = slice_ptr[slice];
+    w = (slice_ptr[slice + 1] - base) >> 5;
+    ib = inc_ptr[row];
+    ie = inc_ptr[row + 1];
+    if (want_J) {
+#pragma unroll
+      for (int k = 0; k < kPre; ++k) pre[k] = k < w ? src[base + 32 * k + (row & 31)] : 0xFFFFFFFFu;
+    }
+  }
+  __syncthreads();
+  if (!has_row) return;
   const bool rbc = sBC[threadIdx.x] != 0;
   double Fr = 0.0, Jd = 0.0;
-  for (int32_t k = inc_ptr[row]; k < inc_ptr[row + 1]; ++k) {
+  for (int32_t k = ib; k < ie; ++k) {
     const uint32_t code = inc_code[k];
     const uint32_t le = code >> 2, a = code & 3u;
     Fr += sK[a * cap + le];
@@ -420,13 +437,8 @@ assemble_blocks_kernel(int32_t n_owned, int32_t rows_per_block, int32_t cap, int
   }
   F[row] = rbc ? sV[VN * vcap + threadIdx.x] - N_bdry : Fr;
   if (!want_J) return;
-  const int32_t slice = row >> 5;
-  const int32_t base = slice_ptr[slice];
-  const int32_t w = (slice_ptr[slice + 1] - base) >> 5;
-  for (int k = 0; k < w; ++k) {
-    const int32_t pos = base + 32 * k + (row & 31);
-    const uint32_t s2 = src[pos];
-    if (s2 == 0xFFFFFFFFu) continue;       // padding
+  auto entry = [&](uint32_t s2, int32_t pos) {
+    if (s2 == 0xFFFFFFFFu) return;         // padding
     double v;
     if (s2 == 0xFFFEFFFEu) v = rbc ? 1.0 : Jd;
     else {
@@ -435,6 +447,13 @@ assemble_blocks_kernel(int32_t n_owned, int32_t rows_per_block, int32_t cap, int
       if (cb != 0xFFFFu) v += sK[(3 + (cb & 15u)) * cap + (cb >> 4)];
     }
     Jval[pos] = v;
+  };
+#pragma unroll
+  for (int k = 0; k < kPre; ++k)
+    if (k < w) entry(pre[k], base + 32 * k + (row & 31));
+  for (int k = kPre; k < w; ++k) {
+    const int32_t pos = base + 32 * k + (row & 31);
+    entry(src[pos], pos);
   }
 }
 
