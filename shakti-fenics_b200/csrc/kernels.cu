@@ -369,6 +369,23 @@ assemble_blocks_kernel(int32_t n_owned, int32_t rows_per_block, int32_t cap, int
   const int32_t r0 = blockIdx.x * rows_per_block;
   const int32_t nrows = min(rows_per_block, n_owned - r0);
   const int32_t h0 = blk_hptr[blockIdx.x], nh = blk_hptr[blockIdx.x + 1] - h0;
+  // cell ids, Kbar and block-local vertex ids of this thread's cells are requested first: the chain
+  // blk_elems -> kbar would otherwise be exposed at the start of every cell (low occupancy)
+  constexpr int kCellsPre = 4;
+  const int32_t e0 = blk_eptr[blockIdx.x], e1 = blk_eptr[blockIdx.x + 1];
+  double kb_pre[kCellsPre];
+  uint32_t lv01_pre[kCellsPre], lv2_pre[kCellsPre];
+#pragma unroll
+  for (int c = 0; c < kCellsPre; ++c) {
+    const int32_t le = threadIdx.x + c * blockDim.x;
+    kb_pre[c] = 0.0; lv01_pre[c] = 0; lv2_pre[c] = 0;
+    if (le < e1 - e0) {
+      const uint16_t* lv = blk_lv + 3 * (size_t)(e0 + le);
+      lv01_pre[c] = (uint32_t)lv[0] | ((uint32_t)lv[1] << 16);
+      lv2_pre[c] = lv[2];
+      kb_pre[c] = kbar[blk_elems[e0 + le]];
+    }
+  }
   // ---- phase 0
   for (int32_t i = threadIdx.x; i < nrows + nh; i += blockDim.x) {
     const int32_t g = i < nrows ? r0 + i : blk_halo[h0 + i - nrows];
@@ -389,14 +406,26 @@ assemble_blocks_kernel(int32_t n_owned, int32_t rows_per_block, int32_t cap, int
   }
   __syncthreads();
   // ---- phase 1
-  const int32_t e0 = blk_eptr[blockIdx.x], e1 = blk_eptr[blockIdx.x + 1];
-  for (int32_t le = threadIdx.x; le < e1 - e0; le += blockDim.x) {
-    const int32_t e = blk_elems[e0 + le];
-    const uint16_t* lv = blk_lv + 3 * (size_t)(e0 + le);
-    const int v[3] = {lv[0], lv[1], lv[2]};
+#pragma unroll 1
+  for (int c = 0; c * (int32_t)blockDim.x + (int32_t)threadIdx.x < e1 - e0; ++c) {
+    const int32_t le = threadIdx.x + c * blockDim.x;
+    int v[3];
+    double kb;
+    if (c < kCellsPre) {
+      uint32_t a01 = lv01_pre[0], a2 = lv2_pre[0];
+      kb = kb_pre[0];
+#pragma unroll
+      for (int q = 1; q < kCellsPre; ++q)
+        if (c == q) { a01 = lv01_pre[q]; a2 = lv2_pre[q]; kb = kb_pre[q]; }
+      v[0] = a01 & 0xFFFFu; v[1] = a01 >> 16; v[2] = a2;
+    } else {
+      const uint16_t* lv = blk_lv + 3 * (size_t)(e0 + le);
+      v[0] = lv[0]; v[1] = lv[1]; v[2] = lv[2];
+      kb = kbar[blk_elems[e0 + le]];
+    }
     ElemOut o;
     double Nv[3];
-    element_FJ_staged(v, sV, vcap, kbar[e], dt, p, o, Nv);
+    element_FJ_staged(v, sV, vcap, kb, dt, p, o, Nv);
     const bool bc[3] = {sBC[v[0]] != 0, sBC[v[1]] != 0, sBC[v[2]] != 0};
     apply_lifting(o, Nv, bc, N_bdry);
 #pragma unroll
