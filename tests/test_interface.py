@@ -160,3 +160,34 @@ def test_synthetic_configs_sizes():
     lake = c5.meta["lake"] > 0
     pulse = configs.lake_pulse_inputs(c5, c5.meta["t_pulse"])
     assert np.allclose(pulse[lake], 11 * c5.meta["inputs0"][lake]) and np.allclose(pulse[~lake], c5.meta["inputs0"][~lake])
+
+
+def test_background_gradient_and_flux_of_linear_head():
+    """grad/dot of the mini-UFL on a linear field: exact constant gradient in every cell."""
+    import constitutive as cst
+    from shakti_b200.ufl_lite import as_expr
+    xy, cells, *_ = make_case(nx=6, ny=4)
+    mesh = fem.Mesh(xy, cells)
+    V = fem.functionspace(mesh, ("CG", 1))
+    zb, zs = fem.Function(V), fem.Function(V)
+    zb.x.array[:] = 3.0 + 0.01 * xy[:, 0]
+    zs.x.array[:] = 3.0 + 0.01 * xy[:, 0] + 1000.0 - 0.02 * xy[:, 1]
+    g = cst.BackgroundGradient(zb, zs)
+    assert np.allclose(g.val[..., 0], 0.01) and np.allclose(g.val[..., 1], -0.02 * 0.917)
+    b = fem.Function(V)
+    b.x.array[:] = 2e-3
+    N = fem.Function(V)
+    qv = fem.Function(fem.functionspace(mesh, fem.element('P', 'triangle', 1, shape=(2,))))
+    q = cst.WaterFlux(b, cst.Head(N, zb, zs), cst.Reynolds(qv))
+    K = cst.Transmissivity(2e-3, 0.0)
+    assert np.allclose(q.val[..., 0], -K * 0.01) and np.allclose(q.val[..., 1], K * 0.02 * 0.917)
+    # Closure is pointwise: A b N |N|^(n-1), signed in b and N
+    N.x.array[:] = -4.0e5
+    c = as_expr(cst.Closure(b, N))
+    assert np.allclose(c.val, cst.A * 2e-3 * (-4.0e5) ** 3)
+
+
+def test_main_usage_error():
+    import subprocess
+    r = subprocess.run([sys.executable, "main.py"], cwd=str(SRC), capture_output=True, text=True)
+    assert r.returncode != 0 and "usage" in (r.stdout + r.stderr)
