@@ -254,7 +254,17 @@ typedef enum shakti_host_array {
   SHAKTI_HM_NBR_RANK = 11,  /* n_nbrs                                                    */
   SHAKTI_HM_NBR_SEND_PTR = 12, /* n_nbrs+1 offsets into SEND_IDX                         */
   SHAKTI_HM_NBR_SEND_IDX = 13, /* owned local ids to send, concatenated per neighbour    */
-  SHAKTI_HM_NBR_RECV = 14   /* 2*n_nbrs: (first ghost local id, count) per neighbour     */
+  SHAKTI_HM_NBR_RECV = 14,  /* 2*n_nbrs: (first ghost local id, count) per neighbour     */
+  /* row-block plan of the atomics-free assembly kernel (csrc/prep.h AssemblyBlocks) */
+  SHAKTI_HM_AB_INFO = 15,   /* rows_per_block, n_blocks, max_cells, max_verts, ok         */
+  SHAKTI_HM_AB_EPTR = 16,   /* n_blocks+1                                                 */
+  SHAKTI_HM_AB_ELEMS = 17,  /* local cell ids per block                                   */
+  SHAKTI_HM_AB_LV = 18,     /* 3 per block cell: block-local vertex index                 */
+  SHAKTI_HM_AB_HPTR = 19,   /* n_blocks+1                                                 */
+  SHAKTI_HM_AB_HALO = 20,   /* halo vertices per block (local ids)                        */
+  SHAKTI_HM_AB_INCPTR = 21, /* n_owned+1                                                  */
+  SHAKTI_HM_AB_INC = 22,    /* (cell index in block)*4 + local vertex index               */
+  SHAKTI_HM_AB_SRC = 23     /* per padded SELL entry: two 16-bit gather codes (as int32 bits) */
 } shakti_host_array;
 /* Size query (out == NULL) or copy of one of the arrays above. */
 int shakti_host_mesh_array(shakti_host_mesh* hm, int which, int32_t* out, int64_t* n);

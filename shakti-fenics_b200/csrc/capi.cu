@@ -1010,7 +1010,11 @@ int shakti_get_owned(shakti_model* m, int32_t* ids, int64_t* n_owned) {
 }
 
 // ---------------------------------------------------------------- host-side helpers
-struct shakti_host_mesh { shakti::HostMesh hm; };
+struct shakti_host_mesh {
+  shakti::HostMesh hm;
+  shakti::AssemblyBlocks ab;
+  bool ab_built = false;
+};
 
 int shakti_host_csr_pattern(int64_t n_vert, int64_t n_cell, const int32_t* cells, int32_t* rowptr, int32_t* col,
                             int64_t* nnz) {
@@ -1084,6 +1088,23 @@ int shakti_host_mesh_array(shakti_host_mesh* h, int which, int32_t* out, int64_t
     case SHAKTI_HM_NBR_RECV:
       for (const auto& nb : m.nbrs) { tmp.push_back(nb.recv_begin); tmp.push_back(nb.recv_count); }
       v = &tmp; break;
+    case SHAKTI_HM_AB_INFO: case SHAKTI_HM_AB_EPTR: case SHAKTI_HM_AB_ELEMS: case SHAKTI_HM_AB_LV: case SHAKTI_HM_AB_HPTR:
+    case SHAKTI_HM_AB_HALO: case SHAKTI_HM_AB_INCPTR: case SHAKTI_HM_AB_INC: case SHAKTI_HM_AB_SRC: {
+      if (!h->ab_built) { build_assembly_blocks(m, 400, h->ab); h->ab_built = true; }
+      const AssemblyBlocks& ab = h->ab;
+      switch (which) {
+        case SHAKTI_HM_AB_INFO: tmp = {ab.rows_per_block, ab.n_blocks, ab.max_cells, ab.max_verts, ab.ok ? 1 : 0}; break;
+        case SHAKTI_HM_AB_EPTR: tmp = ab.blk_eptr; break;
+        case SHAKTI_HM_AB_ELEMS: tmp = ab.blk_elems; break;
+        case SHAKTI_HM_AB_LV: tmp.assign(ab.blk_lv.begin(), ab.blk_lv.end()); break;
+        case SHAKTI_HM_AB_HPTR: tmp = ab.blk_hptr; break;
+        case SHAKTI_HM_AB_HALO: tmp = ab.blk_halo; break;
+        case SHAKTI_HM_AB_INCPTR: tmp = ab.inc_ptr; break;
+        case SHAKTI_HM_AB_INC: tmp.assign(ab.inc_code.begin(), ab.inc_code.end()); break;
+        default: tmp.resize(ab.src.size()); std::memcpy(tmp.data(), ab.src.data(), ab.src.size() * sizeof(uint32_t)); break;
+      }
+      v = &tmp; break;
+    }
     default: throw Error(SHAKTI_ERR_INVALID, "unknown host array id");
   }
   if (out) {

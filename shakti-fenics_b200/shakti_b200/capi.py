@@ -18,7 +18,8 @@ KSP = dict(gmres=0, bicgstab=1)
 PC = dict(jacobi=0, amg=1, none=2)
 NEWTON_R0 = dict(dolfinx=0, initial_residual=1)
 HOST_ARRAYS = dict(l2g=0, cells=1, cell_l2g=2, rowptr=3, col=4, slice_ptr=5, sell_col=6, slot=7, diag_pos=8,
-                   win=9, win_cell=10, nbr_rank=11, nbr_send_ptr=12, nbr_send_idx=13, nbr_recv=14)
+                   win=9, win_cell=10, nbr_rank=11, nbr_send_ptr=12, nbr_send_idx=13, nbr_recv=14,
+                   ab_info=15, ab_eptr=16, ab_elems=17, ab_lv=18, ab_hptr=19, ab_halo=20, ab_incptr=21, ab_inc=22, ab_src=23)
 
 ERR_NOT_CONVERGED = -4
 ERR_LINEAR = -5

@@ -167,3 +167,60 @@ def test_product_never_imports_the_oracle():
     for f in (pkg / "csrc").glob("*"):
         if f.suffix in (".cu", ".cpp", ".h"):
             assert "oracle" not in f.read_text().lower(), f
+
+
+@pytest.mark.parametrize("nranks", [1, 2])
+def test_assembly_row_block_plan_emulated_in_numpy(mesh, nranks):
+    """The plan behind assemble_blocks_kernel (csrc/prep.cpp build_assembly_blocks), executed in numpy exactly
+    as the kernel does -- stage the block's cells, then gather per row through the incident-cell codes and the
+    two-source codes -- must reproduce the plain scatter-add of the cell matrices, with no atomics."""
+    xy, cells = mesh
+    nv = xy.shape[0]
+    o = ShaktiOracle(xy, cells)
+    rng = np.random.default_rng(1)
+    Ke = rng.standard_normal((cells.shape[0], 9))
+    Fe = rng.standard_normal((cells.shape[0], 3))
+    ref = np.zeros(o.col.size)
+    np.add.at(ref, o.slot.ravel(), Ke.ravel())
+    Jref = sp.csr_matrix((ref, o.col, o.rowptr), shape=(nv, nv))
+    Fref = np.zeros(nv)
+    np.add.at(Fref, cells.ravel(), Fe.ravel())
+    for r in range(nranks):
+        hm = capi.HostMesh(xy, cells, r, nranks, 1)
+        rb, nb, max_cells, max_verts, ok = hm.array("ab_info")
+        assert ok == 1 and rb in (32, 64, 128, 256) and max_cells <= 400
+        l2g, lc, cl2g = hm.array("l2g"), hm.array("cells").reshape(-1, 3), hm.array("cell_l2g")
+        eptr, elems, lv = hm.array("ab_eptr"), hm.array("ab_elems"), hm.array("ab_lv").reshape(-1, 3)
+        hptr, halo = hm.array("ab_hptr"), hm.array("ab_halo")
+        incptr, inc = hm.array("ab_incptr"), hm.array("ab_inc")
+        src = hm.array("ab_src").view(np.uint32)
+        sptr, rowptr = hm.array("slice_ptr"), hm.array("rowptr")
+        vals = np.zeros(hm.padded)
+        F = np.zeros(hm.n_owned)
+        assert nb == (hm.n_owned + rb - 1) // rb and eptr[-1] == elems.size
+        for B in range(nb):
+            r0, r1 = B * rb, min(hm.n_owned, (B + 1) * rb)
+            be = elems[eptr[B]:eptr[B + 1]]
+            assert np.all(np.diff(be) > 0)
+            # block-local vertex table = own rows then halo
+            table = np.concatenate([np.arange(r0, r1), halo[hptr[B]:hptr[B + 1]]])
+            assert table.size <= max_verts and np.array_equal(table[lv[eptr[B]:eptr[B + 1]]], lc[be])
+            sK = np.concatenate([Fe[cl2g[be]], Ke[cl2g[be]]], axis=1)       # (cells in block, 12)
+            for row in range(r0, r1):
+                codes = inc[incptr[row]:incptr[row + 1]]
+                le, a = codes >> 2, codes & 3
+                F[row] = sK[le, a].sum()
+                diag = sK[le, 3 + 4 * a].sum()
+                base = sptr[row >> 5] + (row & 31)
+                for k in range(rowptr[row + 1] - rowptr[row]):
+                    pos = base + 32 * k
+                    s2 = int(src[pos])
+                    assert s2 != 0xFFFFFFFF
+                    if s2 == 0xFFFEFFFE:
+                        vals[pos] = diag
+                    else:
+                        ca, cb = s2 & 0xFFFF, s2 >> 16
+                        vals[pos] = sK[ca >> 4, 3 + (ca & 15)] + (sK[cb >> 4, 3 + (cb & 15)] if cb != 0xFFFF else 0.0)
+        own = l2g[: hm.n_owned]
+        assert np.allclose(F, Fref[own], rtol=1e-13, atol=1e-13)
+        assert abs(_sell_to_csr(hm, vals, nv)[own] - Jref[own]).max() < 1e-12
