@@ -268,6 +268,10 @@ typedef enum shakti_host_array {
 } shakti_host_array;
 /* Size query (out == NULL) or copy of one of the arrays above. */
 int shakti_host_mesh_array(shakti_host_mesh* hm, int which, int32_t* out, int64_t* n);
+/* Strength-of-connection filter (|a_ij| >= theta sqrt(|a_ii a_jj|), theta <= 0: all connections) and greedy
+ * aggregation of a square CSR matrix, as the AMG set-up does on each level; agg_out[i] in [0, *n_agg) or -1. */
+int shakti_host_amg_aggregate(int32_t n, const int32_t* rowptr, const int32_t* col, const double* val, double theta,
+                              const uint8_t* exclude, int32_t* agg_out, int32_t* n_agg);
 /* info[0..5] = n_owned, n_local, n_cell_local, nnz_local, padded SELL entries, n_nbrs */
 int shakti_host_mesh_info(shakti_host_mesh* hm, int64_t info[6]);
 

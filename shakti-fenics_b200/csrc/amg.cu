@@ -1107,3 +1107,41 @@ void Amg::apply(const DevSell& Afine, const double* rin, double* z) {
 }
 
 }  // namespace shakti
+
+// ---------------------------------------------------------------- host-only test hook
+// Strength filter + greedy aggregation of a square CSR matrix, exactly as coarsen_level() does on one rank.
+extern "C" int shakti_host_amg_aggregate(int32_t n, const int32_t* rowptr, const int32_t* col, const double* val,
+                                         double theta, const uint8_t* exclude, int32_t* agg_out, int32_t* n_agg) {
+  try {
+    if (n <= 0 || !rowptr || !col || !agg_out || !n_agg) throw shakti::Error(SHAKTI_ERR_INVALID, "bad arguments");
+    shakti::HostCsr A;
+    A.n_rows = A.n_cols = n;
+    A.rowptr.assign(rowptr, rowptr + n + 1);
+    A.col.assign(col, col + rowptr[n]);
+    std::vector<uint8_t> excl;
+    if (exclude) excl.assign(exclude, exclude + n);
+    std::vector<uint8_t> strong;
+    if (theta > 0 && val) {
+      std::vector<double> diag(n, 0.0);
+      for (int32_t i = 0; i < n; ++i)
+        for (int32_t k = rowptr[i]; k < rowptr[i + 1]; ++k)
+          if (col[k] == i) diag[i] = std::fabs(val[k]);
+      strong.assign(A.nnz(), 0);
+      for (int32_t i = 0; i < n; ++i)
+        for (int32_t k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+          const int32_t j = col[k];
+          if (j == i) continue;
+          const double a = std::fabs(val[k]);
+          strong[k] = (a >= theta * std::sqrt(diag[i] * diag[j])) && a > 0;
+        }
+    }
+    std::vector<int32_t> agg;
+    *n_agg = shakti::aggregate(A, n, excl, strong, agg);
+    std::copy(agg.begin(), agg.end(), agg_out);
+    return SHAKTI_OK;
+  } catch (const std::exception& e) {
+    shakti::set_last_error(e.what());
+    return SHAKTI_ERR_INVALID;
+  }
+}
+

@@ -158,6 +158,19 @@ def host_locate_dirichlet(n_vert, cells, marker):
     return out[: n.value].copy()
 
 
+def host_amg_aggregate(A_csr, theta=0.08, exclude=None):
+    """Aggregates of a scipy CSR matrix as the AMG set-up forms them -> (agg ids, count)."""
+    lib = load()
+    n = A_csr.shape[0]
+    rp, col, val = _i32(A_csr.indptr), _i32(A_csr.indices), _f64(A_csr.data)
+    agg = np.empty(n, dtype=np.int32)
+    na = C.c_int32(0)
+    ex = None if exclude is None else np.ascontiguousarray(exclude, dtype=np.uint8)
+    _check(lib.shakti_host_amg_aggregate(C.c_int32(n), _p(rp), _p(col), _p(val), C.c_double(theta),
+                                         _p(ex) if ex is not None else None, _p(agg), C.byref(na)))
+    return agg, na.value
+
+
 class HostMesh:
     """The rank-local mesh the device code works on (host-only; no GPU needed)."""
 
