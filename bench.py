@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--linear-rtol", type=float, default=1e-12)
     ap.add_argument("--amg-refresh-every", type=int, default=None, help="override shakti_options.amg_refresh_every")
     ap.add_argument("--lagged-smoother-halo", action="store_true", help="multi-GPU: amg_smoother_halo = 0")
+    ap.add_argument("--linear-forcing", type=float, default=None, help="override shakti_options.linear_forcing (0 = fixed tolerance)")
     ap.add_argument("--no-graph", action="store_true", help="do not replay the AMG V-cycle as a CUDA graph")
     ap.add_argument("--cpu-sample-nside", type=int, default=None,
                     help="mesh side of the bounded CPU sample (default: sized so that the CPU run takes ~2 minutes)")
@@ -191,6 +192,8 @@ def main():
     case = configs.dofs16m(nside=args.nside, nsteps=nsteps_total)
     nv = case.n_vert
     extra = {} if args.amg_refresh_every is None else {"amg_refresh_every": args.amg_refresh_every}
+    if args.linear_forcing is not None:
+        extra["linear_forcing"] = args.linear_forcing
     if args.no_graph:
         extra["amg_cuda_graph"] = 0
     if args.lagged_smoother_halo:

@@ -82,7 +82,8 @@ typedef struct shakti_options {
   int32_t newton_r0;            /* shakti_newton_r0 */
   int32_t linear_solver;        /* shakti_linear_solver */
   int32_t precond;              /* shakti_precond */
-  double linear_rtol;           /* ||J dx - F_k|| <= linear_rtol * ||F_0|| (F_0: residual the Newton solve started from) */
+  double linear_rtol;           /* floor of the Krylov target: ||J dx - F_k|| <= linear_rtol * ||F_0|| (F_0: residual the Newton
+                                   solve started from); see linear_forcing */
   double linear_atol;
   int32_t linear_max_it;
   int32_t gmres_restart;
@@ -102,6 +103,9 @@ typedef struct shakti_options {
   double b_min;                 /* md.b_min, model_setup.py:53 */
   int32_t assembly_kernel;      /* 0 = row-block staged gather (default), 1 = element atomics */
   int32_t reorder;              /* 1 = internal Morton reordering (default), 0 = keep caller order */
+  double linear_forcing;        /* > 0 (default 0.01): the Krylov solve of a Newton iteration stops at linear_forcing x the
+                                   residual the NEXT Newton iterate is predicted to have (never below linear_rtol ||F_0||, never
+                                   above 1e-2 ||F_k||); 0 = always solve to linear_rtol ||F_0|| (closest to the reference's LU) */
 } shakti_options;
 
 typedef struct shakti_stats {
@@ -134,6 +138,8 @@ int shakti_create(int64_t n_vert, int64_t n_cell, const double* xy, const int32_
 int shakti_destroy(shakti_model* m);
 const char* shakti_last_error(void);
 const char* shakti_version(void);
+/* Number of CUDA devices visible to this process (0 without a driver / device). */
+int shakti_device_count(int* n);
 
 /* ---------------------------------------------------------------- data in / out */
 
@@ -190,6 +196,8 @@ int shakti_newton_solve(shakti_model* m, double dt, int32_t* niter, int32_t* con
 int shakti_update_q(shakti_model* m);
 int shakti_update_melt(shakti_model* m);
 int shakti_update_b(shakti_model* m, double dt);
+/* solvers.py:186 and :189 in one pass over the vertices (same results as the two calls above) */
+int shakti_update_q_melt(shakti_model* m);
 /* solvers.py:228-229 */
 int shakti_copy_N_to_N_n(shakti_model* m);
 /* One whole pass of solvers.py:179-229 (without file output). */
@@ -205,6 +213,26 @@ int shakti_run_timed(shakti_model* m, const double* dts, int64_t nsteps, int32_t
 int shakti_step_host(shakti_model* m, double dt, const double* inputs_host, double* b_out,
                      double* N_out, double* qx_out, double* qy_out, int32_t* niter,
                      int32_t* converged);
+
+/* Asynchronous, double-buffered form of shakti_step_host (the save path of solvers.py:199-225 without
+ * stalling the time loop).  The step itself is complete on return (niter / converged are final); the
+ * device->host copies of b, N, qx, qy into the given buffers (pinned memory for true overlap; any may
+ * be NULL) are only ENQUEUED on a second stream from on-device snapshots, so they overlap the next
+ * step.  The buffers are valid after shakti_wait_outputs(); alternate two buffer sets to keep a step's
+ * output while the next one runs.
+ *   owned_only = 0: buffers hold n_vert doubles in caller numbering (other ranks' entries are 0);
+ *   owned_only = 1: buffers (and inputs_host) hold this rank's n_owned doubles in shakti_get_owned order,
+ *                   so N ranks move 1/N of the bytes each and the caller places them with that index map. */
+int shakti_step_host_async(shakti_model* m, double dt, const double* inputs_host, double* b_out,
+                           double* N_out, double* qx_out, double* qy_out, int owned_only,
+                           int32_t* niter, int32_t* converged);
+int shakti_wait_outputs(shakti_model* m);
+/* The output half alone (for callers that drive the split entry points, as solvers.solve(md) does). */
+int shakti_save_outputs_async(shakti_model* m, double* b_out, double* N_out, double* qx_out, double* qy_out,
+                              int owned_only);
+/* Page-locked host memory for those buffers (cudaMallocHost / cudaFreeHost). */
+int shakti_alloc_pinned(int64_t bytes, void** out);
+int shakti_free_pinned(void* p);
 
 /* ---------------------------------------------------------------- micro-benchmarks
  * Launch one kernel `reps` times on the library stream and return the mean device time per

@@ -201,12 +201,126 @@ amg_spgemm_warp_kernel(SellView A, const int32_t* __restrict__ Alen, SellView B,
   }
 }
 
-// C = A B numerically (pattern of C known), thread-per-row for large matrices, warp-per-row for small ones
-static void spgemm_numeric(const DevSell& A, const DevSell& B, DevSell& C, cudaStream_t s) {
+// ---- table-driven product for the large levels.  The patterns are fixed by the mesh, so the position of
+// every product a_ik b_kj inside C's row is found ONCE (the binary search above, run by
+// amg_spgemm_slots_kernel) and kept as one byte per product, stored slice-interleaved like the matrices:
+// product t of row r at prod_ptr[r >> 5] + 32 t + (r & 31).  The numeric product then streams A, the
+// table and the gathered rows of B, accumulates C's row in shared memory (no global read-modify-write,
+// no search) and writes it once.
+struct SpgemmPlan {
+  bool built = false, ok = false;
+  DevBuf<int64_t> prod_ptr;   // n_slices + 1
+  DevBuf<uint8_t> slot;
+};
+
+// per slice: 32 x (largest number of products of any of its rows)
+__global__ void __launch_bounds__(128)
+amg_spgemm_count_kernel(SellView A, const int32_t* __restrict__ Alen, const int32_t* __restrict__ Blen, int32_t Bn_rows,
+                        int32_t* __restrict__ slice_width) {
+  const int32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+  int32_t cnt = 0;
+  if (row < A.n_rows) {
+    const int32_t abase = A.slice_ptr[row >> 5] + (row & 31);
+    const int32_t alen = Alen[row];
+    for (int ka = 0; ka < alen; ++ka) {
+      const int32_t j = A.col[abase + 32 * ka];
+      if (j < Bn_rows) cnt += Blen[j];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt = max(cnt, __shfl_xor_sync(0xffffffffu, cnt, o));
+  if ((threadIdx.x & 31) == 0 && (row >> 5) < A.n_slices) slice_width[row >> 5] = cnt;
+}
+
+__global__ void __launch_bounds__(128)
+amg_spgemm_slots_kernel(SellView A, const int32_t* __restrict__ Alen, SellView B, const int32_t* __restrict__ Blen,
+                        int32_t Bn_rows, const int32_t* __restrict__ Cslice, const int32_t* __restrict__ Ccol,
+                        const int32_t* __restrict__ Clen, const int64_t* __restrict__ prod_ptr, uint8_t* __restrict__ slot) {
+  const int32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= A.n_rows) return;
+  const int32_t lane = row & 31;
+  const int32_t abase = A.slice_ptr[row >> 5] + lane;
+  const int32_t cbase = Cslice[row >> 5] + lane;
+  const int32_t clen = Clen[row], alen = Alen[row];
+  uint8_t* __restrict__ sp = slot + prod_ptr[row >> 5] + lane;
+  int64_t t = 0;
+  for (int ka = 0; ka < alen; ++ka) {
+    const int32_t j = A.col[abase + 32 * ka];
+    if (j >= Bn_rows) continue;
+    const int32_t bbase = B.slice_ptr[j >> 5] + (j & 31);
+    const int32_t blen = Blen[j];
+    for (int kb = 0; kb < blen; ++kb, ++t) {
+      const int32_t c = B.col[bbase + 32 * kb];
+      int lo = 0, hi = clen - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (Ccol[cbase + 32 * mid] < c) lo = mid + 1; else hi = mid;
+      }
+      sp[32 * t] = (uint8_t)lo;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128)
+amg_spgemm_table_kernel(SellView A, const int32_t* __restrict__ Alen, SellView B, const int32_t* __restrict__ Blen,
+                        int32_t Bn_rows, const int32_t* __restrict__ Cslice, const int32_t* __restrict__ Clen,
+                        const int64_t* __restrict__ prod_ptr, const uint8_t* __restrict__ slot, double* __restrict__ Cval) {
+  extern __shared__ double acc[];   // [C width][128]: entry k of this thread's row at acc[k * 128 + threadIdx.x]
+  const int32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= A.n_rows) return;
+  const int32_t lane = row & 31;
+  const int32_t abase = A.slice_ptr[row >> 5] + lane;
+  const int32_t clen = Clen[row], alen = Alen[row];
+  double* __restrict__ my = acc + threadIdx.x;
+  for (int k = 0; k < clen; ++k) my[k * 128] = 0.0;
+  const uint8_t* __restrict__ sp = slot + prod_ptr[row >> 5] + lane;
+  int64_t t = 0;
+  for (int ka = 0; ka < alen; ++ka) {
+    const int32_t j = A.col[abase + 32 * ka];
+    if (j >= Bn_rows) continue;
+    const double a = A.val[abase + 32 * ka];
+    const int32_t bbase = B.slice_ptr[j >> 5] + (j & 31);
+    const int32_t blen = Blen[j];
+    for (int kb = 0; kb < blen; ++kb, ++t) my[(int)sp[32 * t] * 128] += a * B.val[bbase + 32 * kb];
+  }
+  double* __restrict__ cp = Cval + Cslice[row >> 5] + lane;
+  for (int k = 0; k < clen; ++k) cp[32 * k] = my[k * 128];
+}
+
+static void build_spgemm_plan(const DevSell& A, const DevSell& B, const DevSell& C, SpgemmPlan& plan, cudaStream_t s) {
+  plan.built = true;
+  plan.ok = false;
+  static const bool disabled = getenv("SHAKTI_SPGEMM_SEARCH") != nullptr;   // A/B switch: keep the searching kernels
+  const size_t smem = (size_t)C.max_width * 128 * sizeof(double);
+  if (disabled || A.n_rows == 0 || C.max_width > 255 || smem > 96 * 1024) return;
+  DevBuf<int32_t> width;
+  width.alloc_zero(A.n_slices, s);
+  SHAKTI_LAUNCH(amg_spgemm_count_kernel, div_up((int64_t)A.n_slices * 32, 128), 128, 0, s, view(A), A.rowlen.p, B.rowlen.p, B.n_rows,
+                width.p);
+  const std::vector<int32_t> w = width.download(s);
+  std::vector<int64_t> ptr(w.size() + 1, 0);
+  for (size_t i = 0; i < w.size(); ++i) ptr[i + 1] = ptr[i] + 32 * (int64_t)w[i];
+  plan.prod_ptr.upload(ptr);
+  plan.slot.alloc((size_t)std::max<int64_t>(ptr.back(), 1));
+  SHAKTI_LAUNCH(amg_spgemm_slots_kernel, div_up(A.n_rows, 128), 128, 0, s, view(A), A.rowlen.p, view(B), B.rowlen.p, B.n_rows,
+                C.slice_ptr.p, C.col.p, C.rowlen.p, plan.prod_ptr.p, plan.slot.p);
+  if (smem > 48 * 1024)
+    SHAKTI_CUDA(cudaFuncSetAttribute(amg_spgemm_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  plan.ok = true;
+}
+
+// C = A B numerically (pattern of C known): table-driven thread-per-row for large matrices, warp-per-row for small ones
+static void spgemm_numeric(const DevSell& A, const DevSell& B, DevSell& C, SpgemmPlan& plan, cudaStream_t s) {
   if (A.n_rows == 0) return;
   if (A.n_rows <= 400000) {
     SHAKTI_LAUNCH(amg_spgemm_warp_kernel, div_up((int64_t)A.n_rows * 32, 128), 128, 0, s, view(A), A.rowlen.p, view(B), B.rowlen.p,
                   B.n_rows, C.slice_ptr.p, C.col.p, C.rowlen.p, C.val.p);
+    return;
+  }
+  if (!plan.built) build_spgemm_plan(A, B, C, plan, s);
+  if (plan.ok) {
+    SHAKTI_LAUNCH(amg_spgemm_table_kernel, div_up(A.n_rows, 128), 128, (size_t)C.max_width * 128 * sizeof(double), s, view(A),
+                  A.rowlen.p, view(B), B.rowlen.p, B.n_rows, C.slice_ptr.p, C.rowlen.p, plan.prod_ptr.p, plan.slot.p, C.val.p);
   } else {
     SHAKTI_CUDA(cudaMemsetAsync(C.val.p, 0, sizeof(double) * C.padded, s));
     SHAKTI_LAUNCH(amg_spgemm_kernel, div_up(A.n_rows, 128), 128, 0, s, view(A), A.rowlen.p, view(B), B.rowlen.p, B.n_rows,
@@ -420,6 +534,7 @@ struct AmgLevel {
   DevBuf<int32_t> diag_pos;   // levels >= 1
   DevBuf<double> dinv;
   DevSell P, R, AP;           // P: (n + n_ghost) x (n_coarse + n_coarse_ghost); R = (P[owned, owned])^T
+  SpgemmPlan plan_AP, plan_RAP;
   DevBuf<uint8_t> pmap;
   DevBuf<int32_t> tmap;
   CycleVecs<double> vd;       // V-cycle work vectors, double ...
@@ -547,8 +662,8 @@ static void numeric_level(Amg::Impl& I, size_t l, const DevSell& Afine, const in
   if (L.R.padded)
     SHAKTI_LAUNCH(amg_gather_vals_kernel, (int)std::min<int64_t>(148 * 8, std::max<int64_t>(1, (L.R.padded + 255) / 256)), 256, 0, s,
                   L.R.padded, L.tmap.p, L.P.val.p, L.R.val.p);
-  spgemm_numeric(A, L.P, L.AP, s);                 // A restricted to the columns P has rows for
-  spgemm_numeric(L.R, L.AP, I.lv[l + 1]->A, s);    // Galerkin: R (A P)
+  spgemm_numeric(A, L.P, L.AP, L.plan_AP, s);                 // A restricted to the columns P has rows for
+  spgemm_numeric(L.R, L.AP, I.lv[l + 1]->A, L.plan_RAP, s);    // Galerkin: R (A P)
 }
 
 // Copies the V-cycle reads: smoother diagonal in the cycle's precision and, for the mixed-precision

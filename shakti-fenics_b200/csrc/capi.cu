@@ -16,8 +16,8 @@ namespace shakti {
 static thread_local std::string t_last_error;
 void set_last_error(const std::string& msg) { t_last_error = msg; }
 
-// default degree-7 table: collapsed Gauss-Jacobi 4x4 (stand-in for Basix' default; see
-// shakti_b200/quadrature.py which generates these digits and tests/test_quadrature.py)
+// default degree-7 table: collapsed Gauss-Jacobi 4x4, generated below by Golub-Welsch (stand-in for
+// Basix' default; the CPU checker under tests/ builds the same rule independently and checks its degree)
 static void default_k_rule(std::vector<double>& pts, std::vector<double>& wts);
 }  // namespace shakti
 
@@ -51,6 +51,12 @@ struct shakti_model {
   DevBuf<double> stage2;  // 2 nv_g (interleaved flux)
   DevBuf<double> scal;    // small device scalars
   double* host_scal = nullptr;  // pinned
+  // asynchronous output path (shakti_step_host_async): snapshots of b, N, qx, qy taken on the compute
+  // stream, copied to the caller's host buffers on a second stream while the next step runs
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_snap = nullptr, ev_d2h = nullptr;
+  DevBuf<double> out_stage[4];
+  bool d2h_pending = false;
   double N_bdry = 0.0;
   int64_t n_bc = 0;
   bool h0_dirty = true;
@@ -65,8 +71,11 @@ struct shakti_model {
   bool amg_setup_done = false;
   int64_t step_of_refresh = -1000000;  // st.steps at the last AMG refresh
   int newton_it_in_step = 0;           // Newton iteration index of the solve in progress
-  int its_after_refresh = 0;           // Krylov iterations of the first solve after the last refresh
-  int last_solve_its = 0;
+  double rate_after_refresh = 0.0;     // Krylov iterations per decade of the first solve after the last refresh
+  double last_rate = 0.0;              // ... and of the latest solve
+  // adaptive Krylov tolerance (linear_forcing): contraction r1/r0 of the previous time step's first
+  // Newton iteration and the dt it was observed with (<= 0: nothing known)
+  double hist_ratio = -1.0, hist_dt = 0.0;
   // Newton state
   double residual0 = 0.0;  // DOLFINx NewtonSolver::_residual0 (kept across solves)
   shakti_stats st{};
@@ -128,6 +137,7 @@ static void set_field(shakti_model* m, int f, const double* src, int is_device) 
   }
   scatter_in(m, s, field_ptr(m, f));
   if (f == SHAKTI_F_Z_B || f == SHAKTI_F_Z_S) m->h0_dirty = true;
+  if (f != SHAKTI_F_INPUTS) m->hist_ratio = -1.0;   // state replaced from outside: no convergence history
   if (!is_device) SHAKTI_CUDA(cudaStreamSynchronize(m->stream));
 }
 
@@ -241,19 +251,22 @@ static KrylovResult linear_solve(shakti_model* m, const double* rhs, double* dx,
     // a lagged hierarchy is repeated once with a fresh one.
     const int every = std::max(1, m->opt.amg_refresh_every);
     const bool due = m->newton_it_in_step == 0 && (m->st.steps - m->step_of_refresh) >= every;
-    const bool degraded = m->its_after_refresh > 0 && m->last_solve_its > (3 * m->its_after_refresh) / 2 + 2;
+    // iteration counts are compared per decade of residual reduction: the Krylov tolerance differs from
+    // solve to solve (linear_forcing)
+    const double decades = std::max(1.0, -std::log10(std::max(rtol, 1e-300)));
+    const bool degraded = m->rate_after_refresh > 0 && m->last_rate > 1.5 * m->rate_after_refresh + 0.25;
     auto do_refresh = [&]() {
       m->amg->refresh(m->J, m->diag_pos.p);
       m->st.amg_refreshes++;
       m->step_of_refresh = m->st.steps;
-      m->its_after_refresh = -1;
+      m->rate_after_refresh = -1.0;
     };
     bool fresh = false;
     if (!m->amg->ready() || due || degraded) { do_refresh(); fresh = true; }
     else m->amg->refresh_fine_smoother(m->J, m->diag_pos.p);
     PrecFn M = [m](const double* rr, double* z) { m->amg->apply(m->J, rr, z); };
     int budget = m->opt.linear_max_it;
-    if (!fresh && m->its_after_refresh > 0) budget = std::min(budget, 3 * m->its_after_refresh + 20);
+    if (!fresh && m->rate_after_refresh > 0) budget = std::min(budget, (int)(3.0 * m->rate_after_refresh * decades) + 20);
     r = krylov(M, budget);
     m->st.linear_its += r.iterations;
     if (!r.converged && !fresh) {
@@ -261,6 +274,8 @@ static KrylovResult linear_solve(shakti_model* m, const double* rhs, double* dx,
       r = krylov(M, m->opt.linear_max_it);
       m->st.linear_its += r.iterations;
     }
+    m->last_rate = r.iterations / decades;
+    if (m->rate_after_refresh < 0) m->rate_after_refresh = std::max(0.05, m->last_rate);
   } else {
     PrecFn M;
     if (m->opt.precond == SHAKTI_PC_JACOBI) {
@@ -275,8 +290,6 @@ static KrylovResult linear_solve(shakti_model* m, const double* rhs, double* dx,
     m->st.linear_its += r.iterations;
   }
   m->st.last_linear_relres = r.relres;
-  m->last_solve_its = r.iterations;
-  if (m->its_after_refresh < 0) m->its_after_refresh = std::max(1, r.iterations);
   return r;
 }
 
@@ -288,28 +301,51 @@ __global__ void fix_bc_dx_kernel(int32_t n, const uint8_t* __restrict__ isbc, co
 }
 
 // DOLFINx NewtonSolver::solve (criterion "residual", relaxation 1, LU replaced by Krylov)
+//
+// The reference solves every Newton system exactly (LU).  Here the Krylov solve of Newton iteration k
+// stops at an ABSOLUTE residual tau_k:
+//   linear_forcing == 0 : tau_k = linear_rtol * ||F_0||            (F_0: residual the solve started from)
+//   linear_forcing  > 0 : tau_k = max(linear_rtol ||F_0||, linear_forcing * max(pred_{k+1}, newton target))
+// where pred_{k+1} is the residual an exact Newton step is expected to leave: the quadratic model
+// r_k^3 / r_{k-1}^2 for k >= 1 and, for k = 0, the first contraction r_1/r_0 observed in the previous time
+// step (same dt; nothing known => the tight tolerance).  With linear_forcing = 0.01 the inexactness
+// changes every Newton residual by ~1 %, so the iteration counts and the converged fields are those of
+// the exact iteration (tests: identical Newton counts, fields <= 1e-8 against the CPU LU restatement), at about
+// half the Krylov iterations.
 static void newton_solve(shakti_model* m, double dt, int32_t* niter, int32_t* converged) {
   const int32_t no = m->hm.n_owned;
+  static const bool trace = getenv("SHAKTI_TRACE_NEWTON") != nullptr;
   compute_kbar(m);
   assemble(m, dt, 1);
   double r = norm2(m, m->F.p);
   const double r_init = r;
-  auto check = [&](double res) {
-    double rel;
-    if (m->opt.newton_r0 == SHAKTI_R0_DOLFINX) rel = m->residual0 > 0 ? res / m->residual0 : INFINITY;
-    else rel = r_init > 0 ? res / r_init : 0.0;
-    return rel < m->opt.newton_rtol || res < m->opt.newton_atol;
+  auto rel_of = [&](double res) {
+    if (m->opt.newton_r0 == SHAKTI_R0_DOLFINX) return m->residual0 > 0 ? res / m->residual0 : (double)INFINITY;
+    return r_init > 0 ? res / r_init : 0.0;
+  };
+  auto check = [&](double res) { return rel_of(res) < m->opt.newton_rtol || res < m->opt.newton_atol; };
+  // absolute residual below which the Newton test passes (unknown before the first dx in DOLFINx mode)
+  auto newton_target = [&]() {
+    const double den = m->opt.newton_r0 == SHAKTI_R0_DOLFINX ? m->residual0 : r_init;
+    return std::max(m->opt.newton_atol, den > 0 ? m->opt.newton_rtol * den : 0.0);
   };
   bool conv = check(r);
   int it = 0;
+  double r_prev = -1.0;
+  const double forcing = m->opt.linear_forcing;
+  const bool hist_ok = m->hist_ratio > 0 && m->hist_dt > 0 && std::fabs(dt / m->hist_dt - 1.0) < 0.5;
+  if (trace && comm().rank == 0) fprintf(stderr, "[newton] dt %.4g r0 %.6e\n", dt, r);
   while (!conv && it < m->opt.newton_max_it) {
     // Dirichlet rows are identity rows and their columns are zero: solve the interior system
     launch_xmy_masked(no, m->F.p, m->isbc.p, m->rhs.p, m->stream);
-    // The reference solves each Newton system exactly (LU).  Here the Krylov residual target is
-    // linear_rtol relative to the residual the Newton solve STARTED from, so later iterations
-    // (whose right-hand side is already small) are not over-solved.
     m->newton_it_in_step = it;
-    const double rtol_k = std::min(1e-2, m->opt.linear_rtol * std::max(1.0, r > 0 ? r_init / r : 1.0));
+    double tau = m->opt.linear_rtol * r_init, pred = -1.0;
+    if (forcing > 0) {
+      if (it == 0) { if (hist_ok) pred = std::min(m->hist_ratio, 0.1) * r; }
+      else if (r_prev > 0) pred = r * (r / r_prev) * (r / r_prev);
+      if (pred >= 0) tau = std::max(tau, forcing * std::max(pred, newton_target()));
+    }
+    const double rtol_k = std::min(1e-2, r > 0 ? tau / r : 1e-2);
     KrylovResult kr = linear_solve(m, m->rhs.p, m->dx.p, rtol_k);
     if (!kr.converged)
       throw Error(SHAKTI_ERR_LINEAR, "Krylov solve did not reach its tolerance (relres " +
@@ -319,10 +355,20 @@ static void newton_solve(shakti_model* m, double dt, int32_t* niter, int32_t* co
     m->halo.exchange(m->N.p, m->stream);
     ++it;
     if (it == 1 && m->opt.newton_r0 == SHAKTI_R0_DOLFINX) m->residual0 = norm2(m, m->dx.p);
-    assemble(m, dt, 1);
+    // The Jacobian is only needed if another iteration follows: when the model says this one converged
+    // with a decade to spare, assemble the residual alone (and the Jacobian after all if it did not)
+    const bool expect_conv = forcing > 0 && pred >= 0 && 10.0 * (pred + rtol_k * r) < newton_target();
+    assemble(m, dt, expect_conv ? 0 : 1);
+    r_prev = r;
     r = norm2(m, m->F.p);
     conv = check(r);
+    if (!conv && expect_conv) assemble(m, dt, 1);
+    if (trace && comm().rank == 0)
+      fprintf(stderr, "[newton]   it %d krylov %d (rtol %.2e) r %.6e rel %.3e%s\n", it, kr.iterations, rtol_k, r, rel_of(r),
+              expect_conv ? " F-only" : "");
+    if (it == 1) { m->hist_ratio = r_prev > 0 ? r / r_prev : -1.0; m->hist_dt = dt; }
   }
+  if (it == 0) m->hist_ratio = -1.0;
   m->st.newton_its += it;
   m->st.last_residual = r;
   m->st.last_residual0 = m->opt.newton_r0 == SHAKTI_R0_DOLFINX ? m->residual0 : r_init;
@@ -342,6 +388,14 @@ static void update_melt(shakti_model* m) {
   std::swap(m->melt.p, m->melt2.p);
   m->halo.exchange(m->melt.p, m->stream);
 }
+// q and melt_n in one pass (what shakti_step uses; identical results to update_q + update_melt)
+static void update_q_melt(shakti_model* m) {
+  refresh_h0(m);
+  launch_update_q_melt(m->hm.n_owned, m->win.p, m->x.p, m->y.p, m->h0.p, m->N.p, m->b.p, m->qx.p, m->qy.p, m->G.p,
+                       m->melt.p, m->melt2.p, m->dprm, m->stream);
+  std::swap(m->melt.p, m->melt2.p);
+  m->halo.exchange(m->melt.p, m->stream);
+}
 static void update_b(shakti_model* m, double dt) {
   refresh_h0(m);
   launch_update_b(m->hm.n_owned, m->win.p, m->x.p, m->y.p, m->h0.p, m->N.p, m->b.p, m->qx.p, m->qy.p, m->G.p,
@@ -350,6 +404,9 @@ static void update_b(shakti_model* m, double dt) {
   m->halo.exchange(m->b.p, m->stream);
   m->halo.exchange(m->qx.p, m->stream);
   m->halo.exchange(m->qy.p, m->stream);
+  // the gap-height update closes a time step on both paths (shakti_step and the split entry points
+  // solvers.solve(md) drives), so the step counter -- and with it amg_refresh_every -- advances here
+  m->st.steps++;
 }
 static void copy_N(shakti_model* m) {
   SHAKTI_CUDA(cudaMemcpyAsync(m->N_n.p, m->N.p, sizeof(double) * m->hm.n_local, cudaMemcpyDeviceToDevice, m->stream));
@@ -359,13 +416,42 @@ static void step(shakti_model* m, double dt, int32_t* niter, int32_t* converged)
   SHAKTI_REQUIRE(dt > 0, "dt must be positive");
   int32_t it = 0, cv = 0;
   newton_solve(m, dt, &it, &cv);
-  update_q(m);
-  update_melt(m);
+  update_q_melt(m);
   update_b(m, dt);
   copy_N(m);
-  m->st.steps++;
   if (niter) *niter = it;
   if (converged) *converged = cv;
+}
+
+// Snapshot b, N, qx, qy on the compute stream and enqueue their device->host copies on the copy stream
+// (see shakti_step_host_async in the header).
+static void save_outputs_async(shakti_model* m, double* b_out, double* N_out, double* qx_out, double* qy_out, int owned_only) {
+  const HostMesh& hm = m->hm;
+  const size_t n_out = owned_only ? (size_t)hm.n_owned : (size_t)hm.nv_g;
+  double* outs[4] = {b_out, N_out, qx_out, qy_out};
+  const double* src[4] = {m->b.p, m->N.p, m->qx.p, m->qy.p};
+  bool any = false;
+  for (int k = 0; k < 4; ++k) any |= outs[k] != nullptr;
+  if (!any) return;
+  // the previous snapshots must have left the device before they are overwritten (a D2H of the
+  // previous save is far shorter than a step, so this wait is free in practice)
+  if (m->d2h_pending) SHAKTI_CUDA(cudaStreamWaitEvent(m->stream, m->ev_d2h, 0));
+  for (int k = 0; k < 4; ++k) {
+    if (!outs[k]) continue;
+    if (m->out_stage[k].n < n_out) m->out_stage[k].alloc(std::max<size_t>(n_out, 1));
+    if (owned_only) {
+      if (n_out) SHAKTI_CUDA(cudaMemcpyAsync(m->out_stage[k].p, src[k], sizeof(double) * n_out, cudaMemcpyDeviceToDevice, m->stream));
+    } else {
+      gather_out(m, src[k], m->out_stage[k].p);
+    }
+  }
+  SHAKTI_CUDA(cudaEventRecord(m->ev_snap, m->stream));
+  SHAKTI_CUDA(cudaStreamWaitEvent(m->copy_stream, m->ev_snap, 0));
+  for (int k = 0; k < 4; ++k)
+    if (outs[k] && n_out)
+      SHAKTI_CUDA(cudaMemcpyAsync(outs[k], m->out_stage[k].p, sizeof(double) * n_out, cudaMemcpyDeviceToHost, m->copy_stream));
+  SHAKTI_CUDA(cudaEventRecord(m->ev_d2h, m->copy_stream));
+  m->d2h_pending = true;
 }
 
 static void set_dirichlet(shakti_model* m, const int32_t* dofs, int64_t n, double value) {
@@ -378,6 +464,7 @@ static void set_dirichlet(shakti_model* m, const int32_t* dofs, int64_t n, doubl
   m->isbc.upload(flag);
   m->N_bdry = value;
   m->n_bc = n;   // global count: >0 on every rank
+  m->hist_ratio = -1.0;
   m->amg_setup_done = false;  // excluded rows changed
   m->amg.reset();
 }
@@ -405,6 +492,9 @@ static void create(int64_t nv, int64_t ne, const double* xy, const int32_t* cell
     throw Error(SHAKTI_ERR_NO_DEVICE, std::string("device '") + prop.name + "' is not sm_100 class; this library is built for sm_100a only");
   m->sm_count = prop.multiProcessorCount;
   SHAKTI_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  SHAKTI_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+  SHAKTI_CUDA(cudaEventCreateWithFlags(&m->ev_snap, cudaEventDisableTiming));
+  SHAKTI_CUDA(cudaEventCreateWithFlags(&m->ev_d2h, cudaEventDisableTiming));
   if (params) m->prm = *params; else shakti_default_params(&m->prm);
   if (opt) m->opt = *opt; else shakti_default_options(&m->opt);
   m->dprm = make_dev_params(m->prm);
@@ -478,6 +568,9 @@ static void destroy(shakti_model* m) {
   if (m->stream) cudaStreamSynchronize(m->stream);
   // swap-safe: DevBuf destructors free whatever pointer they currently hold
   if (m->host_scal) cudaFreeHost(m->host_scal);
+  if (m->copy_stream) { cudaStreamSynchronize(m->copy_stream); cudaStreamDestroy(m->copy_stream); }
+  if (m->ev_snap) cudaEventDestroy(m->ev_snap);
+  if (m->ev_d2h) cudaEventDestroy(m->ev_d2h);
   cudaStream_t s = m->stream;
   delete m;
   if (s) cudaStreamDestroy(s);
@@ -586,6 +679,13 @@ extern "C" {
 const char* shakti_last_error(void) { return shakti::t_last_error.c_str(); }
 const char* shakti_version(void) { return "shakti_b200 0.1 (sm_100a)"; }
 
+int shakti_device_count(int* n) {
+  if (!n) return SHAKTI_ERR_INVALID;
+  *n = 0;
+  if (cudaGetDeviceCount(n) != cudaSuccess) { cudaGetLastError(); *n = 0; }
+  return SHAKTI_OK;
+}
+
 int shakti_default_params(shakti_params* p) {
   if (!p) return SHAKTI_ERR_INVALID;
   p->g = 9.81; p->rho_i = 917; p->rho_w = 1000; p->nu = 1.787e-6; p->Lh = 3.34e5; p->omega = 1e-3; p->n = 3; p->A = 2.24e-24;
@@ -601,6 +701,7 @@ int shakti_default_options(shakti_options* o) {
   o->amg_smoother_omega = 0.67; o->amg_prolong_omega = 0.67; o->amg_strength_theta = 0.08; o->amg_cheby_ratio = 5.0;
   o->amg_smoother = 1; o->amg_fp32_cycle = 1; o->amg_cuda_graph = 1; o->amg_smoother_halo = 1;
   o->b_min = 1.0e-5; o->assembly_kernel = 0; o->reorder = 1;
+  o->linear_forcing = 0.01;
   return SHAKTI_OK;
 }
 
@@ -636,6 +737,7 @@ int shakti_set_flux(shakti_model* m, const double* q, int is_device) {
   SHAKTI_TRY
   SHAKTI_REQUIRE(m && q, "null argument");
   use_device(m);
+  m->hist_ratio = -1.0;
   const int64_t nv = m->hm.nv_g;
   if (!m->stage2.p) m->stage2.alloc((size_t)3 * nv);
   const double* src = q;
@@ -712,6 +814,7 @@ int shakti_set_options(shakti_model* m, const shakti_options* opt) {
   SHAKTI_REQUIRE(opt->reorder == m->opt.reorder, "reorder can only be chosen at create time");
   const int restart_old = m->opt.gmres_restart;
   m->opt = *opt;
+  m->hist_ratio = -1.0;
   if (amg_changed) { m->amg.reset(); m->amg_setup_done = false; }
   if (opt->gmres_restart != restart_old)
     m->gmres.init(m->hm.n_owned, m->hm.n_local, std::max(2, opt->gmres_restart), m->sm_count, m->stream);
@@ -861,6 +964,13 @@ int shakti_update_melt(shakti_model* m) {
   update_melt(m);
   SHAKTI_CATCH
 }
+int shakti_update_q_melt(shakti_model* m) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(m, "null model");
+  use_device(m);
+  update_q_melt(m);
+  SHAKTI_CATCH
+}
 int shakti_update_b(shakti_model* m, double dt) {
   SHAKTI_TRY
   SHAKTI_REQUIRE(m && dt > 0, "bad arguments");
@@ -933,6 +1043,60 @@ int shakti_step_host(shakti_model* m, double dt, const double* inputs_host, doub
   SHAKTI_CATCH
 }
 
+int shakti_wait_outputs(shakti_model* m) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(m, "null model");
+  use_device(m);
+  if (m->d2h_pending) {
+    SHAKTI_CUDA(cudaEventSynchronize(m->ev_d2h));
+    m->d2h_pending = false;
+  }
+  SHAKTI_CATCH
+}
+
+int shakti_step_host_async(shakti_model* m, double dt, const double* inputs_host, double* b_out, double* N_out,
+                           double* qx_out, double* qy_out, int owned_only, int32_t* niter, int32_t* converged) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(m, "null model");
+  use_device(m);
+  const HostMesh& hm = m->hm;
+  if (inputs_host) {
+    if (owned_only) {
+      // this rank's entries, in shakti_get_owned order, straight into the field; ghosts from their owners
+      SHAKTI_CUDA(cudaMemcpyAsync(m->inputs.p, inputs_host, sizeof(double) * hm.n_owned, cudaMemcpyHostToDevice, m->stream));
+      m->halo.exchange(m->inputs.p, m->stream);
+    } else {
+      SHAKTI_CUDA(cudaMemcpyAsync(m->stage.p, inputs_host, sizeof(double) * hm.nv_g, cudaMemcpyHostToDevice, m->stream));
+      scatter_in(m, m->stage.p, m->inputs.p);
+    }
+  }
+  shakti::step(m, dt, niter, converged);
+  shakti::save_outputs_async(m, b_out, N_out, qx_out, qy_out, owned_only);
+  SHAKTI_CATCH
+}
+
+int shakti_save_outputs_async(shakti_model* m, double* b_out, double* N_out, double* qx_out, double* qy_out,
+                              int owned_only) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(m, "null model");
+  use_device(m);
+  shakti::save_outputs_async(m, b_out, N_out, qx_out, qy_out, owned_only);
+  SHAKTI_CATCH
+}
+
+int shakti_alloc_pinned(int64_t bytes, void** out) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(out && bytes >= 0, "bad arguments");
+  *out = nullptr;
+  if (bytes) SHAKTI_CUDA(cudaMallocHost(out, (size_t)bytes));
+  SHAKTI_CATCH
+}
+int shakti_free_pinned(void* p) {
+  SHAKTI_TRY
+  if (p) SHAKTI_CUDA(cudaFreeHost(p));
+  SHAKTI_CATCH
+}
+
 int shakti_kernel_bytes(shakti_model* m, int which, double* bytes) {
   if (!m || !bytes) return SHAKTI_ERR_INVALID;
   const double nv = (double)m->hm.n_local, no = (double)m->hm.n_owned, ne = (double)m->hm.ne, nnz = (double)m->hm.A.nnz();
@@ -962,8 +1126,9 @@ int shakti_time_kernel(shakti_model* m, int which, int reps, double dt, double* 
       case 1: assemble(m, dt, 1); break;
       case 2: compute_kbar(m); break;
       case 3:
-        // same kernels as a step, on scratch outputs so the state is untouched
-        launch_update_melt(m->hm.n_owned, m->win.p, m->x.p, m->y.p, m->h0.p, m->N.p, m->b.p, m->qx.p, m->qy.p, m->G.p, m->melt.p, m->melt2.p, m->dprm, m->stream);
+        // the two kernels of a step's nodal pass (q + melt fused, then b), all outputs to scratch
+        // vectors so the state is untouched
+        launch_update_q_melt(m->hm.n_owned, m->win.p, m->x.p, m->y.p, m->h0.p, m->N.p, m->b.p, m->dx.p, m->rhs.p, m->G.p, m->melt.p, m->melt2.p, m->dprm, m->stream);
         launch_update_b(m->hm.n_owned, m->win.p, m->x.p, m->y.p, m->h0.p, m->N.p, m->b.p, m->qx.p, m->qy.p, m->G.p, m->melt.p, m->b2.p, dt, m->opt.b_min, m->dprm, m->stream);
         break;
       case 4: launch_multi_dot(m->red, m->hm.n_owned, 1, m->dx.p, m->hm.n_owned, m->rhs.p, m->scal.p, m->stream); break;

@@ -19,6 +19,7 @@ DevParams make_dev_params(const shakti_params& p);
 // SELL-32 sparse matrix on the device (layout: prep.h HostSell)
 struct DevSell {
   int32_t n_rows = 0, n_cols = 0, n_slices = 0;
+  int32_t max_width = 0;        // longest row
   int64_t padded = 0, nnz = 0;
   DevBuf<int32_t> slice_ptr, col, rowlen;
   DevBuf<double> val;
@@ -80,6 +81,10 @@ void launch_update_melt(int32_t n_owned, const int32_t* win, const double* x, co
                         const double* h0, const double* N, const double* b, const double* qx,
                         const double* qy, const double* G, const double* melt_old, double* melt_new,
                         DevParams p, cudaStream_t s);
+// q and melt_n in one pass (same results as launch_update_q followed by launch_update_melt)
+void launch_update_q_melt(int32_t n_owned, const int32_t* win, const double* x, const double* y,
+                          const double* h0, const double* N, const double* b, double* qx, double* qy,
+                          const double* G, const double* melt_old, double* melt_new, DevParams p, cudaStream_t s);
 void launch_update_b(int32_t n_owned, const int32_t* win, const double* x, const double* y,
                      const double* h0, const double* N, const double* b_old, const double* qx,
                      const double* qy, const double* G, const double* melt, double* b_new, double dt,

@@ -2,6 +2,8 @@
 // Jacobian assembly, nodal updates, SELL SpMV family and the vector kernels of the Krylov
 // solvers.  All fp64 / int32, HBM-bandwidth bound by design (no tensor cores: nothing here is
 // a dense contraction).  Reference formulas: source/constitutive.py:6-31, source/solvers.py:35-45.
+#include <algorithm>
+
 #include "device.h"
 
 namespace shakti {
@@ -24,6 +26,8 @@ DevParams make_dev_params(const shakti_params& p) {
 void DevSell::upload_pattern(const HostSell& h, int64_t nnz_) {
   n_rows = (int32_t)h.n_rows; n_cols = (int32_t)h.n_cols; n_slices = (int32_t)h.n_slices;
   padded = h.padded(); nnz = nnz_;
+  max_width = 0;
+  for (int32_t l : h.rowlen) max_width = std::max(max_width, l);
   slice_ptr.upload(h.slice_ptr);
   col.upload(h.col);
   rowlen.upload(h.rowlen);
@@ -635,6 +639,55 @@ void launch_update_b(int32_t n_owned, const int32_t* win, const double* x, const
   if (n_owned == 0) return;
   SHAKTI_LAUNCH(update_b_kernel, div_up(n_owned, 256), 256, 0, s, n_owned, win, x, y, h0, N, b_old, qx, qy, G,
                 melt, b_new, dt, b_min, p);
+}
+
+// Fused pass 1 of the nodal updates: q and melt_n in one kernel (solvers.py:186,189).  The melt update at
+// vertex i needs the NEW flux at i only, so both come from one load of the winning cell, one geometry
+// and one head gradient.  (The gap-height update needs the new melt at the cell's other vertices and
+// therefore stays a second pass.)
+__global__ void __launch_bounds__(256)
+update_q_melt_kernel(int32_t n_owned, const int32_t* __restrict__ win, const double* __restrict__ x,
+                     const double* __restrict__ y, const double* __restrict__ h0, const double* __restrict__ N,
+                     const double* __restrict__ b, double* __restrict__ qx, double* __restrict__ qy,
+                     const double* __restrict__ G, const double* __restrict__ melt_old, double* __restrict__ melt_new,
+                     DevParams p) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_owned) return;
+  const WinGeo w = win_geometry(win, i, x, y);
+  if (w.loc < 0) { melt_new[i] = melt_old[i]; return; }
+  double h[3], bb[3], mm[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    h[a] = h0[w.v[a]] - N[w.v[a]] / p.rwg;
+    bb[a] = b[w.v[a]];
+    mm[a] = melt_old[w.v[a]];
+  }
+  double ghx, ghy, gbx, gby, gmx, gmy;
+  cell_grad(w, h, ghx, ghy);
+  cell_grad(w, bb, gbx, gby);
+  cell_grad(w, mm, gmx, gmy);
+  // the vertex's own values are those of its slot in the winning cell
+  const double b_i = w.loc == 0 ? bb[0] : (w.loc == 1 ? bb[1] : bb[2]);
+  const double m_i = w.loc == 0 ? mm[0] : (w.loc == 1 ? mm[1] : mm[2]);
+  const double bi = fabs(b_i);
+  const double qxo = qx[i], qyo = qy[i];
+  const double Re = sqrt(qxo * qxo + qyo * qyo) / p.nu;
+  const double p1 = -(bi * bi * bi) * p.g;
+  const double p2 = 12.0 * p.nu * (1.0 + p.omega * Re);
+  const double qxn = p1 * ghx / p2, qyn = p1 * ghy / p2;
+  qx[i] = qxn;
+  qy[i] = qyn;
+  const double gb2 = gbx * gbx + gby * gby;
+  const double m0 = (G[i] - p.rwg * (qxn * ghx + qyn * ghy)) / p.Lh;
+  const double md = (gb2 * m_i + b_i * (gmx * gbx + gmy * gby)) / (1.0 + gb2);
+  melt_new[i] = m0 + md;
+}
+void launch_update_q_melt(int32_t n_owned, const int32_t* win, const double* x, const double* y, const double* h0,
+                          const double* N, const double* b, double* qx, double* qy, const double* G,
+                          const double* melt_old, double* melt_new, DevParams p, cudaStream_t s) {
+  if (n_owned == 0) return;
+  SHAKTI_LAUNCH(update_q_melt_kernel, div_up(n_owned, 256), 256, 0, s, n_owned, win, x, y, h0, N, b, qx, qy, G,
+                melt_old, melt_new, p);
 }
 
 // ------------------------------------------------------------------ SELL-32 SpMV family

@@ -50,6 +50,7 @@ class Options(C.Structure):
         ("amg_smoother", C.c_int32), ("amg_fp32_cycle", C.c_int32),
         ("amg_cuda_graph", C.c_int32), ("amg_smoother_halo", C.c_int32),
         ("b_min", C.c_double), ("assembly_kernel", C.c_int32), ("reorder", C.c_int32),
+        ("linear_forcing", C.c_double),
     ]
 
 
@@ -96,6 +97,12 @@ def _i32(a):
 
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+def device_count():
+    n = C.c_int(0)
+    _check(load().shakti_device_count(C.byref(n)))
+    return n.value
 
 
 def default_params():
@@ -196,6 +203,26 @@ class HostMesh:
         if getattr(self, "_h", None) and _lib is not None:
             _lib.shakti_host_mesh_destroy(self._h)
             self._h = None
+
+
+class PinnedArray:
+    """A float64 numpy array over page-locked host memory (cudaMallocHost), freed with the object."""
+
+    def __init__(self, n):
+        self._lib = load()
+        self._ptr = C.c_void_p()
+        _check(self._lib.shakti_alloc_pinned(C.c_int64(8 * max(int(n), 1)), C.byref(self._ptr)))
+        buf = (C.c_double * max(int(n), 1)).from_address(self._ptr.value)
+        self.array = np.frombuffer(buf, dtype=np.float64)[: int(n)]
+
+    def __del__(self):
+        try:
+            if getattr(self, "_ptr", None) and self._ptr.value:
+                self.array = None
+                self._lib.shakti_free_pinned(self._ptr)
+                self._ptr = C.c_void_p()
+        except Exception:
+            pass
 
 
 # ---------------------------------------------------------------------------- multi-GPU
@@ -361,6 +388,9 @@ class Model:
     def update_melt(self):
         _check(self.lib.shakti_update_melt(self._h))
 
+    def update_q_melt(self):
+        _check(self.lib.shakti_update_q_melt(self._h))
+
     def update_b(self, dt):
         _check(self.lib.shakti_update_b(self._h, C.c_double(dt)))
 
@@ -393,6 +423,21 @@ class Model:
         _check(self.lib.shakti_step_host(self._h, C.c_double(dt), vp(inputs_ptr), vp(b_ptr), vp(N_ptr), vp(qx_ptr),
                                          vp(qy_ptr), C.byref(it), C.byref(cv)))
         return it.value, bool(cv.value)
+
+    def step_host_async(self, dt, inputs_ptr=None, b_ptr=None, N_ptr=None, qx_ptr=None, qy_ptr=None, owned_only=False):
+        """shakti_step_host_async: the D2H copies are only enqueued; call wait_outputs() before reading."""
+        it, cv = C.c_int32(0), C.c_int32(0)
+        vp = lambda p: C.c_void_p(p) if p else None
+        _check(self.lib.shakti_step_host_async(self._h, C.c_double(dt), vp(inputs_ptr), vp(b_ptr), vp(N_ptr), vp(qx_ptr),
+                                               vp(qy_ptr), C.c_int(1 if owned_only else 0), C.byref(it), C.byref(cv)))
+        return it.value, bool(cv.value)
+
+    def wait_outputs(self):
+        _check(self.lib.shakti_wait_outputs(self._h))
+
+    def save_outputs_async(self, b, N, qx, qy, owned_only=False):
+        """Enqueue snapshots of b, N, qx, qy into the given (pinned) numpy arrays; valid after wait_outputs()."""
+        _check(self.lib.shakti_save_outputs_async(self._h, _p(b), _p(N), _p(qx), _p(qy), C.c_int(1 if owned_only else 0)))
 
     # ---- micro-benchmarks
     KERNELS = dict(spmv=0, assemble=1, kbar=2, nodal=3, dot=4, axpy=5)

@@ -50,6 +50,18 @@ def get_bcs(md):
 _comm_ready = False
 
 
+def _local_device(md):
+    """The GPU of this process, decided ONCE and used for both the NCCL communicator and the model:
+    LOCAL_RANK (torchrun), else OMPI_COMM_WORLD_LOCAL_RANK (mpirun, as the reference is launched),
+    else rank modulo the number of visible devices; a single process keeps the current device (-1)."""
+    if md.size == 1:
+        return -1
+    for var in ("LOCAL_RANK", "OMPI_COMM_WORLD_LOCAL_RANK", "SLURM_LOCALID"):
+        if os.environ.get(var, "") != "":
+            return int(os.environ[var])
+    return md.rank % max(capi.device_count(), 1)
+
+
 def _ensure_device_comm(md):
     """One NCCL communicator per process group, created once (replaces MPI.COMM_WORLD inside
     DOLFINx/PETSc).  The 128-byte id is broadcast with the host communicator."""
@@ -58,7 +70,7 @@ def _ensure_device_comm(md):
         return
     uid = capi.comm_unique_id() if md.rank == 0 else None
     uid = md.comm.bcast(uid, root=0)
-    capi.comm_init(uid, md.rank, md.size, int(os.environ.get("LOCAL_RANK", md.rank)))
+    capi.comm_init(uid, md.rank, md.size, _local_device(md))
     _comm_ready = True
 
 
@@ -81,7 +93,7 @@ class B200NewtonSolver:
         self.N, self.N_n, self.b, self.q, self.melt_n = N, N_n, b, q, melt_n
         opts = dict(b_min=float(md.b_min))
         opts.update(getattr(md, "solver_options", {}) or {})
-        device = int(os.environ.get("LOCAL_RANK", "0")) if md.size > 1 else -1
+        device = _local_device(md)
         self.model = capi.Model(md.domain.geometry.x[:, :2], md.domain.cells,
                                 params=capi.params_from_module(params), device=device, **opts)
         m = self.model
@@ -142,9 +154,17 @@ class B200NewtonSolver:
     STATE = ("N", "N_n", "b", "melt_n")
 
     def checkpoint(self, path, step):
-        """Write the full device state (extension: the reference can only be restarted from scratch)."""
+        """Write the full device state (extension: the reference can only be restarted from scratch).
+        On several GPUs every rank contributes its owned entries and rank 0 writes the one file, so a run
+        can be resumed on any number of GPUs."""
         m = self.model
-        np.savez(path, step=step, q=m.get_flux(), **{k: m.get_field(k) for k in self.STATE})
+        names = list(self.STATE) + ["qx", "qy"]
+        full = _sum_over_ranks(self.md, [m.get_field(k) for k in names])
+        if self.md.rank == 0:
+            d = dict(zip(names, full))
+            q = np.stack([d.pop("qx"), d.pop("qy")], axis=1)
+            np.savez(path, step=step, q=q, **d)
+        self.md.comm.barrier()
 
     def restore(self, path):
         """Load a state written by ``checkpoint``; returns the index of the last completed step."""
@@ -159,6 +179,45 @@ class B200NewtonSolver:
         its owned entries and zeros elsewhere (summed by the caller)."""
         m = self.model
         return m.get_field("b"), m.get_field("N"), m.get_field("qx"), m.get_field("qy")
+
+
+class _AsyncSaver:
+    """The save path of reference solvers.py:199-225 without stalling the time loop: every rank
+    snapshots its OWNED slice of b, N, qx, qy on the device and copies it into one of two pinned host
+    buffer sets on a side stream while the next steps run (shakti_save_outputs_async); the rows reach the
+    (nti, nd) arrays on rank 0 when the following save -- or a checkpoint, or the end of the run -- needs
+    the buffers back."""
+
+    def __init__(self, md, model):
+        self.md, self.model = md, model
+        self.owned = model.owned()                       # caller ids of this rank's dofs, device order
+        self.all_owned = md.comm.gather(self.owned, root=0)
+        self.sets = [[capi.PinnedArray(self.owned.size) for _ in range(4)] for _ in range(2)]
+        self.pending = None                              # (row j, buffer set)
+        self.k = 0
+
+    def enqueue(self, j):
+        bufs = self.sets[self.k]
+        self.model.save_outputs_async(*[b.array for b in bufs], owned_only=True)
+        self.pending = (j, self.k)
+        self.k ^= 1
+
+    def flush(self, arrays):
+        """Wait for the pending copies and place them in row j of the four (nti, nd) arrays (rank 0)."""
+        if self.pending is None:
+            return
+        j, k = self.pending
+        self.pending = None
+        self.model.wait_outputs()
+        mine = [b.array for b in self.sets[k]]
+        if self.md.size == 1:
+            parts = [mine]
+        else:
+            parts = self.md.comm.gather([a.copy() for a in mine], root=0)
+        if self.md.rank == 0:
+            for ids, part in zip(self.all_owned, parts):
+                for arr, vals in zip(arrays, part):
+                    arr[j, ids] = vals
 
 
 def pde_solver(md, N, N_n, b, q, melt_n, storage, dt):
@@ -253,6 +312,10 @@ def solve(md):
     solver = pde_solver(md, N, N_n, b, q, melt_n, storage, dt)
     solver.sync_host = False            # state stays on the device between saves
     md.solver = solver
+    saver = _AsyncSaver(md, solver.model)
+    out_arrays = (b_arr, N_arr, qx_arr, qy_arr) if md.rank == 0 else None
+    if md.rank != 0:
+        j = 0
 
     # extensions (off unless the setup sets them): md.inputs_of_t(t) -> nodal array for time-dependent
     # forcing, md.resume = True to continue from <results>/checkpoint.npz written every nt_check saves
@@ -267,7 +330,7 @@ def solve(md):
                 if os.path.exists(old):
                     prev = np.load(old)
                     arr[:min(arr.shape[0], prev.shape[0])] = prev[:arr.shape[0]]
-            j = len(range(0, first, md.nt_save))
+        j = len(range(0, first, md.nt_save))
 
     for i in range(first, nt):
 
@@ -292,27 +355,30 @@ def solve(md):
         solver.update_b()
 
         if i % md.nt_save == 0:
-            out = _sum_over_ranks(md, solver.fields_for_output())
+            # the previous save's rows come home now (their copies overlapped the steps in between),
+            # then this step's fields are snapshotted on the device and start their way to the host
+            saver.flush(out_arrays)
+            saver.enqueue(j)
 
-            if md.rank == 0:
-                b_arr[j, :], N_arr[j, :], qx_arr[j, :], qy_arr[j, :] = out
-
-                if i % md.nt_check == 0:
-                    # checkpoint: lets plots be made while the run is in progress
+            if i % md.nt_check == 0:
+                # checkpoint: lets plots be made while the run is in progress (needs this row now)
+                saver.flush(out_arrays)
+                if md.rank == 0:
                     np.save(md.results_name + '/b.npy', b_arr)
                     np.save(md.results_name + '/N.npy', N_arr)
                     np.save(md.results_name + '/qx.npy', qx_arr)
                     np.save(md.results_name + '/qy.npy', qy_arr)
 
-                j += 1
+            j += 1
 
-            if i % md.nt_check == 0 and getattr(md, "resume", False) and md.size == 1:
+            if i % md.nt_check == 0 and getattr(md, "resume", False):
                 solver.copy_N_to_N_n()          # the checkpoint holds the state the next step starts from
                 solver.checkpoint(ckpt, i)
 
         # previous-step solution
         solver.copy_N_to_N_n()
 
+    saver.flush(out_arrays)
     if md.rank == 0:
         np.save(md.results_name + '/b.npy', b_arr)
         np.save(md.results_name + '/N.npy', N_arr)

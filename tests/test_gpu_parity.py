@@ -247,3 +247,133 @@ def test_step_host_matches_step_and_get_field():
             assert np.array_equal(got.numpy(), ref)
     finally:
         m1.close(); m2.close()
+
+
+# ---------------------------------------------------------------------------- round 2
+PARAM_SETS = {
+    # constants of source/params.py:4-11 changed one family at a time; "glen-2.5"/"glen-4" leave the n == 3
+    # fast path and run the general closure branch (pow) of the element kernel and of the b update
+    "flow-law": dict(omega=3.0e-3, A=6.7e-24, nu=2.5e-6),
+    "densities": dict(rho_i=900.0, rho_w=1028.0, g=9.8, Lh=3.0e5),
+    "glen-2.5": dict(n=2.5, A=1.3e-21),
+    "glen-4": dict(n=4.0, A=6.0e-30),
+}
+
+
+@pytest.mark.parametrize("name", list(PARAM_SETS))
+def test_non_default_params_reach_every_kernel(name):
+    """Row a1: params.py constants are kernel ARGUMENTS (never compiled in) -- Kbar, F, J, the three
+    nodal updates and a transient run with modified constants against the oracle with the same ones."""
+    from oracle.shakti_oracle import Params
+    from shakti_b200 import capi
+    over = PARAM_SETS[name]
+    c = make_case(seed=21)
+    o = make_oracle(*c, params=Params(**over))
+    prm = capi.default_params()
+    for k, v in over.items():
+        setattr(prm, k, v)
+    m = make_model(*c, params=prm)
+    o_def = make_oracle(*c)
+    try:
+        assert relinf(m.kbar(), o.kbar()) < 1e-13
+        F, J = m.assemble(DT)
+        Fo, Jo = o.assemble(DT)
+        assert relinf(F, Fo) < 1e-12 and relinf(J, Jo) < 1e-12
+        Fd, _ = o_def.assemble(DT)
+        assert relinf(Fo, Fd) > 1e-6                       # the constants really change the answer
+        dts = [360.0, DT, DT]
+        its_o = [o.step(dt)[0] for dt in dts]
+        its_m = list(m.run(dts))
+        assert its_m == its_o
+        for k, ref in (("N", o.N), ("b", o.b), ("melt_n", o.melt_n)):
+            assert relinf(m.get_field(k), ref) < 1e-8, k
+        assert relinf(m.get_flux(), o.q) < 1e-8
+        # nodal updates alone, from identical state
+        o.N = o.N * 1.01
+        m.set_field("N", o.N)
+        o.update_q(); o.update_melt(); o.update_b(DT)
+        m.update_q(); m.update_melt(); m.update_b(DT)
+        assert relinf(m.get_flux(), o.q) < 1e-12
+        assert relinf(m.get_field("melt_n"), o.melt_n) < 1e-12
+        assert relinf(m.get_field("b"), o.b) < 1e-12
+    finally:
+        m.close()
+
+
+def test_fused_q_melt_update_equals_the_two_calls():
+    c = make_case(seed=22)
+    m1, m2 = make_model(*c), make_model(*c)
+    try:
+        N = c[2]["N_n"] * (1 + 0.01 * np.random.default_rng(1).standard_normal(c[0].shape[0]))
+        for m in (m1, m2):
+            m.set_field("N", N)
+        m1.update_q(); m1.update_melt()
+        m2.update_q_melt()
+        assert relinf(m2.get_flux(), m1.get_flux()) < 1e-15
+        assert relinf(m2.get_field("melt_n"), m1.get_field("melt_n")) < 1e-14
+    finally:
+        m1.close(); m2.close()
+
+
+@pytest.mark.parametrize("forcing", [0.0, 0.01])
+def test_krylov_forcing_keeps_newton_counts_and_fields(forcing):
+    """linear_forcing: the adaptive Krylov tolerance must not change what the Newton iteration does --
+    same iteration counts as the LU oracle and fields within 1e-8, with fewer Krylov iterations."""
+    c = make_case(nx=48, ny=32, seed=23)
+    o = make_oracle(*c)
+    m = make_model(*c, linear_forcing=forcing)
+    try:
+        dts = [360.0] + [DT] * 7
+        its_o = [o.step(dt)[0] for dt in dts]
+        its_m = list(m.run(dts))
+        assert its_m == its_o
+        assert relinf(m.get_field("N"), o.N) < 1e-8 and relinf(m.get_field("b"), o.b) < 1e-8
+        st = m.stats()
+        assert st["steps"] == len(dts)
+        test_krylov_forcing_keeps_newton_counts_and_fields.its[forcing] = st["linear_its"]
+        if len(test_krylov_forcing_keeps_newton_counts_and_fields.its) == 2:
+            k = test_krylov_forcing_keeps_newton_counts_and_fields.its
+            assert k[0.01] < k[0.0], k
+    finally:
+        m.close()
+
+
+test_krylov_forcing_keeps_newton_counts_and_fields.its = {}
+
+
+def test_async_outputs_equal_get_field():
+    """shakti_step_host_async + shakti_wait_outputs: double-buffered pinned host buffers hold exactly what
+    get_field returns after the same step, in caller numbering and as the owned slice."""
+    from shakti_b200 import capi
+    c = make_case(seed=24)
+    m1, m2 = make_model(*c), make_model(*c)
+    try:
+        nv = c[0].shape[0]
+        own = m2.owned()
+        assert np.array_equal(np.sort(own), np.arange(nv))
+        sets = [[capi.PinnedArray(nv) for _ in range(4)] for _ in range(2)]
+        inp = capi.PinnedArray(nv)
+        kept = []
+        for k, dt in enumerate([360.0, DT, DT]):
+            inp.array[:] = c[2]["inputs"] * (1.0 + 0.25 * k)
+            owned_only = k == 2
+            if owned_only:
+                inp.array[:] = (c[2]["inputs"] * (1.0 + 0.25 * k))[own]
+            bufs = sets[k % 2]
+            it2, cv2 = m2.step_host_async(dt, inp.array.ctypes.data, *[b.array.ctypes.data for b in bufs], owned_only=owned_only)
+            m1.set_field("inputs", c[2]["inputs"] * (1.0 + 0.25 * k))
+            it1, cv1 = m1.step(dt)
+            assert (it1, cv1) == (it2, cv2)
+            q = m1.get_flux()
+            kept.append((bufs, owned_only, [m1.get_field("b"), m1.get_field("N"), q[:, 0].copy(), q[:, 1].copy()]))
+            if k >= 1:      # the previous step's buffers are read while this step's copies may still be in flight
+                pb, po, pref = kept[k - 1]
+                m2.wait_outputs()
+                for got, ref in zip(pb, pref):
+                    assert np.array_equal(got.array, ref[own] if po else ref)
+        m2.wait_outputs()
+        pb, po, pref = kept[-1]
+        for got, ref in zip(pb, pref):
+            assert np.array_equal(got.array, ref[own] if po else ref)
+    finally:
+        m1.close(); m2.close()

@@ -114,7 +114,9 @@ def test_main_cli(tmp_path):
         "def initialize(comm):\n"
         "    case = configs.rect_steady(nx=40, ny=20, nsteps=8)\n"
         f"    return md_from_case(comm, case, __file__, nt_save=4, results_name={str(tmp_path / 'out')!r})\n")
-    env = dict(**__import__("os").environ, PYTHONPATH=str(tmp_path))
+    import os
+    # extend, never replace: CI / driver hooks may already export PYTHONPATH
+    env = {**os.environ, "PYTHONPATH": os.pathsep.join(filter(None, [str(tmp_path), os.environ.get("PYTHONPATH")]))}
     r = subprocess.run([sys.executable, "main.py", "setup_cli_case"], cwd=str(src), env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     N = np.load(tmp_path / "out" / "N.npy")
@@ -158,3 +160,30 @@ def test_time_dependent_inputs_and_resume(tmp_path):
     N2, b2 = np.load(tmp_path / "resumed" / "N.npy"), np.load(tmp_path / "resumed" / "b.npy")
     assert N2.shape == N_ref.shape
     assert relinf(N2[-1], N_ref[-1]) < 1e-8 and relinf(b2[-1], b_ref[-1]) < 1e-8
+
+
+def test_step_counter_and_amg_refresh_policy_on_the_split_path(tmp_path):
+    """solvers.solve(md) drives newton_solve / update_* separately: the library's step counter (and with it
+    amg_refresh_every) must advance exactly as it does through shakti_run."""
+    import solvers
+    from shakti_b200 import capi, configs
+    md, case = build_md(tmp_path)
+    md.solver_options = dict(amg_refresh_every=2)
+    solvers.solve(md)
+    st = md.solver.model.stats()
+    nt = md.timesteps.size
+    assert st["steps"] == nt
+    m = capi.Model(case.xy, case.cells, amg_refresh_every=2, b_min=float(md.b_min))
+    try:
+        configs.apply_case(m, case)
+        bc = solvers.get_bcs(md)[0].dofs
+        m.set_dirichlet(bc, md.N_bdry)
+        m.start()
+        dts = np.concatenate([[0.1 * 3600.0], np.full(nt - 1, 3600.0)])
+        m.run(dts)
+        st2 = m.stats()
+        assert st2["steps"] == nt
+        assert abs(st["amg_refreshes"] - st2["amg_refreshes"]) <= 1, (st["amg_refreshes"], st2["amg_refreshes"])
+        assert nt // 2 <= st2["amg_refreshes"] < nt
+    finally:
+        m.close()
