@@ -305,13 +305,16 @@ __global__ void fix_bc_dx_kernel(int32_t n, const uint8_t* __restrict__ isbc, co
 // The reference solves every Newton system exactly (LU).  Here the Krylov solve of Newton iteration k
 // stops at an ABSOLUTE residual tau_k:
 //   linear_forcing == 0 : tau_k = linear_rtol * ||F_0||            (F_0: residual the solve started from)
-//   linear_forcing  > 0 : tau_k = max(linear_rtol ||F_0||, linear_forcing * max(pred_{k+1}, newton target))
+//   linear_forcing  > 0 : tau_k = max(linear_rtol ||F_0||, linear_forcing * pred_{k+1})  while another
+//                         Newton iteration is expected to follow, and linear_rtol ||F_0|| for the solve that
+//                         is expected to be the LAST one (pred_{k+1} within a decade of the Newton target)
 // where pred_{k+1} is the residual an exact Newton step is expected to leave: the quadratic model
 // r_k^3 / r_{k-1}^2 for k >= 1 and, for k = 0, the first contraction r_1/r_0 observed in the previous time
 // step (same dt; nothing known => the tight tolerance).  With linear_forcing = 0.01 the inexactness
-// changes every Newton residual by ~1 %, so the iteration counts and the converged fields are those of
-// the exact iteration (tests: identical Newton counts, fields <= 1e-8 against the CPU LU restatement), at about
-// half the Krylov iterations.
+// changes the intermediate Newton residuals by ~1 % (errors of earlier iterates are damped quadratically)
+// and the final iterate is solved as tightly as before, so the iteration counts and the converged fields
+// are those of the exact iteration (tests: identical Newton counts, fields <= 1e-8 against the CPU LU
+// restatement) at roughly 60 % of the Krylov iterations.
 static void newton_solve(shakti_model* m, double dt, int32_t* niter, int32_t* converged) {
   const int32_t no = m->hm.n_owned;
   static const bool trace = getenv("SHAKTI_TRACE_NEWTON") != nullptr;
@@ -343,7 +346,7 @@ static void newton_solve(shakti_model* m, double dt, int32_t* niter, int32_t* co
     if (forcing > 0) {
       if (it == 0) { if (hist_ok) pred = std::min(m->hist_ratio, 0.1) * r; }
       else if (r_prev > 0) pred = r * (r / r_prev) * (r / r_prev);
-      if (pred >= 0) tau = std::max(tau, forcing * std::max(pred, newton_target()));
+      if (pred >= 10.0 * newton_target()) tau = std::max(tau, forcing * pred);
     }
     const double rtol_k = std::min(1e-2, r > 0 ? tau / r : 1e-2);
     KrylovResult kr = linear_solve(m, m->rhs.p, m->dx.p, rtol_k);
@@ -357,7 +360,7 @@ static void newton_solve(shakti_model* m, double dt, int32_t* niter, int32_t* co
     if (it == 1 && m->opt.newton_r0 == SHAKTI_R0_DOLFINX) m->residual0 = norm2(m, m->dx.p);
     // The Jacobian is only needed if another iteration follows: when the model says this one converged
     // with a decade to spare, assemble the residual alone (and the Jacobian after all if it did not)
-    const bool expect_conv = forcing > 0 && pred >= 0 && 10.0 * (pred + rtol_k * r) < newton_target();
+    const bool expect_conv = forcing > 0 && pred >= 0 && 10.0 * (pred + tau) < newton_target();
     assemble(m, dt, expect_conv ? 0 : 1);
     r_prev = r;
     r = norm2(m, m->F.p);
