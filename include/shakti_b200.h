@@ -106,6 +106,8 @@ typedef struct shakti_options {
   double linear_forcing;        /* > 0 (default 0.01): the Krylov solve of a Newton iteration stops at linear_forcing x the
                                    residual the NEXT Newton iterate is predicted to have (never below linear_rtol ||F_0||, never
                                    above 1e-2 ||F_k||); 0 = always solve to linear_rtol ||F_0|| (closest to the reference's LU) */
+  int32_t amg_replicate_below;  /* multi-GPU: the first AMG level with at most this many rows in total, and every level below
+                                   it, is replicated on all ranks and solved without communication (default 100000) */
 } shakti_options;
 
 typedef struct shakti_stats {

@@ -404,38 +404,53 @@ __global__ void amg_dense_apply_kernel(int32_t n, const double* __restrict__ D, 
 
 // ------------------------------------------------------------------ smoother kernels
 // Chebyshev step: r = dinv (b - A x); d = c1 d + c2 r; x_out = x + d
-template <class T>
+// KG as in spmv_sell_kernel (kernels.cu): 1 = thread per row, 8 = block per slice for small wide-rowed levels
+template <class T, int KG>
 __global__ void __launch_bounds__(256)
 amg_cheby_kernel(SellViewT<T> A, const T* __restrict__ dinv, const T* __restrict__ b, const T* __restrict__ x,
                  T* __restrict__ d, T* __restrict__ x_out, T c1, T c2) {
-  const int32_t row = blockIdx.x * blockDim.x + threadIdx.x;
-  const int32_t slice = row >> 5;
-  if (slice >= A.n_slices) return;
-  const int32_t base = A.slice_ptr[slice];
-  const int32_t w = (A.slice_ptr[slice + 1] - base) >> 5;
-  const int32_t* __restrict__ cp = A.col + base + (row & 31);
-  const T* __restrict__ vp = A.val + base + (row & 31);
+  int32_t row;
   T acc = 0;
+  if (KG == 1) {
+    row = blockIdx.x * blockDim.x + threadIdx.x;
+    const int32_t slice = row >> 5;
+    if (slice >= A.n_slices) return;
+    const int32_t base = A.slice_ptr[slice];
+    const int32_t w = (A.slice_ptr[slice + 1] - base) >> 5;
+    const int32_t* __restrict__ cp = A.col + base + (row & 31);
+    const T* __restrict__ vp = A.val + base + (row & 31);
 #pragma unroll 4
-  for (int k = 0; k < w; ++k) acc += vp[32 * k] * x[cp[32 * k]];
+    for (int k = 0; k < w; ++k) acc += vp[32 * k] * x[cp[32 * k]];
+  } else {
+    __shared__ T psum[KG][32];
+    const int32_t slice = blockIdx.x;
+    const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+    row = slice * 32 + lane;
+    const int32_t base = A.slice_ptr[slice];
+    const int32_t w = (A.slice_ptr[slice + 1] - base) >> 5;
+    const int32_t* __restrict__ cp = A.col + base + lane;
+    const T* __restrict__ vp = A.val + base + lane;
+    for (int k = g; k < w; k += KG) acc += vp[32 * k] * x[cp[32 * k]];
+    psum[g][lane] = acc;
+    __syncthreads();
+    if (g != 0) return;
+#pragma unroll
+    for (int j = 1; j < KG; ++j) acc += psum[j][lane];
+  }
   if (row >= A.n_rows) return;
   const T r = dinv[row] * (b[row] - acc);
   const T dn = c1 * d[row] + c2 * r;
   d[row] = dn;
   x_out[row] = x[row] + dn;
 }
+constexpr int32_t kChebyWideRowsBelow = 300000;
 template <class T>
-static void launch_cheby(SellViewT<T> A, const T* dinv, const T* b, const T* x, T* d, T* x_out, double c1, double c2, cudaStream_t s);
-template <>
-void launch_cheby<double>(SellViewT<double> A, const double* dinv, const double* b, const double* x, double* d, double* x_out,
-                          double c1, double c2, cudaStream_t s) {
-  SHAKTI_LAUNCH((amg_cheby_kernel<double>), div_up((int64_t)A.n_slices * 32, 256), 256, 0, s, A, dinv, b, x, d, x_out, c1, c2);
-}
-template <>
-void launch_cheby<float>(SellViewT<float> A, const float* dinv, const float* b, const float* x, float* d, float* x_out,
-                         double c1, double c2, cudaStream_t s) {
+static void launch_cheby(SellViewT<T> A, const T* dinv, const T* b, const T* x, T* d, T* x_out, double c1, double c2, cudaStream_t s) {
   // (a variant interleaving two slices per warp was measured slower: 193 vs 179 ms per step)
-  SHAKTI_LAUNCH((amg_cheby_kernel<float>), div_up((int64_t)A.n_slices * 32, 256), 256, 0, s, A, dinv, b, x, d, x_out, (float)c1, (float)c2);
+  if (A.n_rows < kChebyWideRowsBelow)
+    SHAKTI_LAUNCH((amg_cheby_kernel<T, 8>), A.n_slices, 256, 0, s, A, dinv, b, x, d, x_out, (T)c1, (T)c2);
+  else
+    SHAKTI_LAUNCH((amg_cheby_kernel<T, 1>), div_up((int64_t)A.n_slices * 32, 256), 256, 0, s, A, dinv, b, x, d, x_out, (T)c1, (T)c2);
 }
 
 // first Chebyshev step from a zero guess: d = (dinv b)/theta ; x = d
@@ -505,13 +520,21 @@ __global__ void amg_dense_assemble_kernel(int32_t N, int32_t nmax, int32_t nrank
   if (j == 0) D[(size_t)gi * 2 * N + N + gi] = 1.0;
 }
 // gathered rhs blocks [rank][nmax] -> global vector
+template <class TO>
 __global__ void amg_compact_kernel(int32_t N, int32_t nmax, int32_t nranks, const int32_t* __restrict__ off,
-                                   const double* __restrict__ G, double* __restrict__ out) {
+                                   const double* __restrict__ G, TO* __restrict__ out) {
   const int32_t gi = blockIdx.x * blockDim.x + threadIdx.x;
   if (gi >= N) return;
   int r = 0;
   while (r + 1 < nranks && off[r + 1] <= gi) ++r;
-  out[gi] = G[(size_t)r * nmax + (gi - off[r])];
+  out[gi] = (TO)G[(size_t)r * nmax + (gi - off[r])];
+}
+
+// out[i] = src[map[i]]
+template <class T>
+__global__ void amg_gather_map_kernel(int32_t n, const int32_t* __restrict__ map, const T* __restrict__ src, T* __restrict__ out) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = src[map[i]];
 }
 
 template <class TI, class TO>
@@ -579,6 +602,29 @@ struct Amg::Impl {
   bool warm = false;           // one plain cycle after a (re)build so that lazy allocations are done
   int64_t graph_launches = 0;  // kernels inside the graph (for the launch accounting)
   void* result_ptr = nullptr;  // where level 0's solution ends up
+  // ---- replicated coarse part (multi-GPU).  Below ~1e5 rows a level is pure latency: a handful of
+  // microsecond kernels separated by halo exchanges.  From `tail_level` on, every rank therefore holds
+  // the WHOLE level (values all-gathered at each refresh) and a complete serial sub-hierarchy `tail`
+  // built from it -- identical on all ranks, no communication.  Per V-cycle one all-gather of the
+  // level's right-hand side remains; the prolongation above it needs no exchange because every rank has
+  // the whole coarse solution.
+  int tail_level = -1;
+  std::unique_ptr<Amg> tail;
+  HostCsr tailA;                 // global pattern of the level (rows and columns in global numbering)
+  HostSell tailS;
+  DevSell tailM;                 // its values
+  DevBuf<int32_t> tail_diag;     // SELL positions of the diagonal
+  int32_t tail_N = 0, tail_nmax = 0, tail_wmax = 0;
+  DevBuf<int32_t> tail_pack_pos;     // [n][wmax] of my rows: position in the level's SELL values (or -1)
+  DevBuf<int32_t> tail_unpack_pos;   // [rank][nmax][wmax]: position in tailM.val (or -1)
+  DevBuf<double> tail_send, tail_recv;
+  DevBuf<int32_t> tail_gid;          // local column (own + ghost) of the level -> global row id
+  DevBuf<int32_t> tail_off;          // first global id of every rank (n_ranks + 1)
+  HaloPlan tail_halo;                // empty plan handed to the (serial) tail
+  std::vector<Neighbor> no_nbrs;
+  int sm_count = 148;
+  P2pGather tail_gather;             // right-hand side all-gather through the symmetric heap
+  DevBuf<double> tail_rhs_d, tail_gather_d;   // NCCL fallback: padded blocks
   ~Impl() {
     if (host_scal) cudaFreeHost(host_scal);
     if (gexec) cudaGraphExecDestroy(gexec);
@@ -587,7 +633,8 @@ struct Amg::Impl {
 
 Amg::Amg() : p_(new Impl()) {}
 Amg::~Amg() = default;
-int Amg::levels() const { return (int)p_->lv.size(); }
+int Amg::levels() const { return (int)p_->lv.size() + (p_->tail ? p_->tail->levels() - 1 : 0); }
+bool Amg::fp32() const { return p_->opt.fp32_cycle != 0; }
 double Amg::operator_complexity() const { return p_->op_complexity; }
 
 static std::vector<int32_t> diag_positions(const HostCsr& A, const HostSell& S, int32_t n) {
@@ -617,6 +664,9 @@ void Amg::setup(const HostCsr& A0, const HostSell& S0, const std::vector<uint8_t
   I.graph_valid = false;
   I.warm = false;
   I.red.init(sm_count);
+  I.sm_count = sm_count;
+  I.tail.reset();
+  I.tail_level = -1;
   I.scal.alloc_zero(4, s);
   if (!I.host_scal) SHAKTI_CUDA(cudaMallocHost(&I.host_scal, 4 * sizeof(double)));
   refreshes_ = 0;
@@ -940,6 +990,123 @@ static void coarsen_level(Amg::Impl& I, size_t l, const DevSell& dA, const HostC
   I.lv.push_back(std::move(Ln));
 }
 
+// Makes level l the root of the replicated part of the hierarchy (see Amg::Impl::tail): gathers the
+// level's pattern from all ranks in a global numbering (ranks in order), builds the maps that move its
+// values at every refresh, and sets up a serial Amg on it.
+static void build_tail(Amg::Impl& I, size_t l) {
+  cudaStream_t s = I.s;
+  AmgLevel& L = *I.lv[l];
+  const HostCsr& A = (l == 0) ? *I.A0 : L.hA;
+  const HostSell& S = (l == 0) ? *I.S0 : L.hS;
+  const int me = comm().rank, nr = comm().nranks;
+  const int32_t n = L.n;
+  const std::vector<double> counts = comm_host_allgather((double)n, s);
+  std::vector<int32_t> off(nr + 1, 0), cnt(nr, 0);
+  int32_t nmax = 1;
+  for (int r = 0; r < nr; ++r) {
+    cnt[r] = (int32_t)counts[r];
+    off[r + 1] = off[r] + cnt[r];
+    nmax = std::max(nmax, cnt[r]);
+  }
+  const int32_t N = off[nr];
+  // global id of every local column: own rows by offset, ghosts from their owners
+  std::vector<int32_t> gid(std::max(L.n_cols, 1), 0);
+  {
+    std::vector<double> tmp((size_t)std::max(L.n_cols, 1), 0.0);
+    for (int32_t c = 0; c < n; ++c) tmp[c] = (double)(off[me] + c);
+    DevBuf<double> dv;
+    dv.upload(tmp);
+    L.halo->exchange(dv.p, s);
+    tmp = dv.download(s);
+    for (int32_t c = 0; c < L.n_cols; ++c) gid[c] = (int32_t)tmp[c];
+  }
+  int32_t wloc = 1;
+  for (int32_t i = 0; i < n; ++i) wloc = std::max(wloc, A.rowptr[i + 1] - A.rowptr[i]);
+  const int32_t wmax = (int32_t)comm_host_max((double)wloc, s);
+  // my rows (length, then global columns in local CSR order) to every rank
+  std::vector<double> mine;
+  mine.reserve((size_t)n + A.nnz());
+  for (int32_t i = 0; i < n; ++i) {
+    mine.push_back((double)(A.rowptr[i + 1] - A.rowptr[i]));
+    for (int32_t k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k) mine.push_back((double)gid[A.col[k]]);
+  }
+  const std::vector<std::vector<double>> in = comm_exchange_lists(std::vector<std::vector<double>>(nr, mine), s);
+  HostCsr& G = I.tailA;
+  G = HostCsr();
+  G.n_rows = G.n_cols = N;
+  G.rowptr.assign((size_t)N + 1, 0);
+  std::vector<int32_t> order;   // for every gathered entry (rank-major, CSR order): its place in the sorted global row
+  std::vector<std::pair<int32_t, int32_t>> tmp;
+  for (int r = 0; r < nr; ++r) {
+    const std::vector<double>& v = in[r];
+    size_t p = 0;
+    for (int32_t i = 0; i < cnt[r]; ++i) {
+      const int len = (int)v[p++];
+      tmp.clear();
+      for (int k = 0; k < len; ++k) tmp.push_back({(int32_t)v[p++], k});
+      std::sort(tmp.begin(), tmp.end());
+      const size_t base = order.size();
+      order.resize(base + len);
+      for (int q = 0; q < len; ++q) {
+        G.col.push_back(tmp[q].first);
+        order[base + tmp[q].second] = q;
+      }
+      G.rowptr[(size_t)off[r] + i + 1] = (int32_t)G.col.size();
+    }
+  }
+  I.tailS = sell_from_csr(G);
+  std::vector<int32_t> unpack((size_t)nr * nmax * wmax, -1), pack((size_t)nmax * wmax, -1);
+  {
+    size_t e = 0;
+    for (int r = 0; r < nr; ++r)
+      for (int32_t i = 0; i < cnt[r]; ++i) {
+        const int32_t gr = off[r] + i;
+        const int len = G.rowptr[gr + 1] - G.rowptr[gr];
+        for (int k = 0; k < len; ++k, ++e) unpack[((size_t)r * nmax + i) * wmax + k] = (int32_t)I.tailS.pos(gr, order[e]);
+      }
+  }
+  for (int32_t i = 0; i < n; ++i)
+    for (int32_t k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k) pack[(size_t)i * wmax + (k - A.rowptr[i])] = (int32_t)S.pos(i, k - A.rowptr[i]);
+  I.tail_N = N; I.tail_nmax = nmax; I.tail_wmax = wmax;
+  I.tail_pack_pos.upload(pack);
+  I.tail_unpack_pos.upload(unpack);
+  I.tail_send.alloc_zero((size_t)nmax * wmax, s);
+  I.tail_recv.alloc_zero((size_t)nr * nmax * wmax, s);
+  I.tail_gid.upload(gid);
+  I.tail_off.upload(off);
+  I.tailM.upload_pattern(I.tailS, G.nnz());
+  I.tail_diag.upload(diag_positions(G, I.tailS, N));
+  if (comm().p2p) {
+    I.tail_gather.build(nmax, s);
+    I.tail_gather.set_counts(cnt);
+  } else {
+    I.tail_rhs_d.alloc_zero(nmax, s);
+    I.tail_gather_d.alloc_zero((size_t)nr * nmax, s);
+  }
+  AmgOptions to = I.opt;
+  to.cuda_graph = 0;   // its kernels are captured as part of the distributed cycle's graph
+  I.tail.reset(new Amg());
+  I.tail_level = (int)l;
+  {
+    CommSerialScope serial;
+    I.tail->setup(I.tailA, I.tailS, std::vector<uint8_t>(), I.no_nbrs, &I.tail_halo, to, I.sm_count, s);
+  }
+}
+
+// all-gather the replicated level's values and renew the serial sub-hierarchy below it
+static void refresh_tail(Amg::Impl& I, const DevSell& Afine) {
+  if (!I.tail) return;
+  cudaStream_t s = I.s;
+  const DevSell& A = (I.tail_level == 0) ? Afine : I.lv[I.tail_level]->A;
+  const int64_t blk = (int64_t)I.tail_nmax * I.tail_wmax;
+  SHAKTI_LAUNCH(amg_pack_rows_kernel, div_up(blk, 256), 256, 0, s, blk, I.tail_pack_pos.p, A.val.p, I.tail_send.p);
+  comm_allgather(I.tail_send.p, I.tail_recv.p, (int)blk, s);
+  const int64_t tot = blk * comm().nranks;
+  SHAKTI_LAUNCH(amg_unpack_rows_kernel, div_up(tot, 256), 256, 0, s, tot, I.tail_unpack_pos.p, I.tail_recv.p, I.tailM.val.p);
+  CommSerialScope serial;
+  I.tail->refresh(I.tailM, I.tail_diag.p);
+}
+
 static void build_hierarchy(Amg::Impl& I, const DevSell& Afine, const int32_t* fine_diag_pos) {
   cudaStream_t s = I.s;
   const AmgOptions& opt = I.opt;
@@ -965,9 +1132,17 @@ static void build_hierarchy(Amg::Impl& I, const DevSell& Afine, const int32_t* f
     nnz_sum += (double)A.nnz();
     const double n_glob = comm_host_sum((double)L.n, s);
     bool stop = (n_glob <= opt.coarse_size) || ((int)l + 1 >= opt.max_levels);
+    // multi-GPU: small levels are replicated (at the latest the level where coarsening ends, unless it is huge)
+    if (comm().active() && n_glob <= std::max(opt.replicate_below, opt.coarse_size)) {
+      build_tail(I, l);
+      L.last = true;
+      numeric_level(I, l, Afine, fine_diag_pos);
+      break;
+    }
     bool stalled = false;
     if (!stop) coarsen_level(I, l, dA, A, S, excl, stalled);
     if (stop || stalled) {
+      if (comm().active() && n_glob <= 4.0e6) build_tail(I, l);
       L.last = true;
       numeric_level(I, l, Afine, fine_diag_pos);
       break;
@@ -985,7 +1160,7 @@ static void build_hierarchy(Amg::Impl& I, const DevSell& Afine, const int32_t* f
     nmax = std::max<int64_t>(nmax, (int64_t)counts[r]);
   }
   N = off.back();
-  I.dense_coarse = N <= 1024 && N > 0;
+  I.dense_coarse = N <= 1024 && N > 0 && !I.tail;
   if (I.dense_coarse) {
     const int me = comm().rank, nr = comm().nranks;
     I.cN = (int32_t)N;
@@ -1019,6 +1194,13 @@ static void build_hierarchy(Amg::Impl& I, const DevSell& Afine, const int32_t* f
   nnz_sum = comm_host_sum(nnz_sum, s);
   I.op_complexity = nnz0 > 0 ? nnz_sum / nnz0 : 0.0;
   I.built = true;
+  if (I.tail) {
+    // the tail's own hierarchy is built by its first refresh (values needed): done right away so that the
+    // level count and the complexity are final when this returns
+    refresh_tail(I, Afine);
+    const double nnz_root = (double)I.tailA.nnz();
+    if (nnz0 > 0) I.op_complexity += (I.tail->operator_complexity() - 1.0) * nnz_root / nnz0;
+  }
 }
 
 // Cheap per-solve update when the hierarchy itself is kept (lagged): the fine-level smoother must
@@ -1048,8 +1230,10 @@ void Amg::refresh(const DevSell& Afine, const int32_t* fine_diag_pos) {
   cudaStream_t s = I.s;
   I.graph_valid = false;
   if (!I.built) { build_hierarchy(I, Afine, fine_diag_pos); I.warm = false; }
-  else
+  else {
     for (size_t l = 0; l < I.lv.size(); ++l) numeric_level(I, l, Afine, fine_diag_pos);
+    refresh_tail(I, Afine);
+  }
   update_smoother_bounds(I, Afine);
   for (size_t l = 0; l < I.lv.size(); ++l) sync_cycle_precision(I, l, Afine, true);
   if (I.dense_coarse) {
@@ -1122,6 +1306,26 @@ static void vcycle(Amg::Impl& I, const DevSell& Afine) {
     AmgLevel& L = *I.lv[l];
     CycleVecs<T>& v = vecs<T>(L);
     const DevSell& A = (l == 0) ? Afine : L.A;
+    if (l == I.tail_level) {
+      // replicated part: all-gather this level's right-hand side, solve on every rank, pick own + ghost entries
+      T* tb = I.tail->rhs_buffer<T>();
+      if (comm().p2p) {
+        I.tail_gather.allgatherv<T, T>(v.b.p, tb, s);
+      } else {
+        SHAKTI_CUDA(cudaMemsetAsync(I.tail_rhs_d.p, 0, sizeof(double) * I.tail_nmax, s));
+        if (L.n) SHAKTI_LAUNCH((amg_convert_kernel<T, double>), div_up(L.n, 256), 256, 0, s, L.n, v.b.p, I.tail_rhs_d.p);
+        comm_allgather(I.tail_rhs_d.p, I.tail_gather_d.p, I.tail_nmax, s);
+        SHAKTI_LAUNCH((amg_compact_kernel<T>), div_up(I.tail_N, 128), 128, 0, s, I.tail_N, I.tail_nmax, comm().nranks, I.tail_off.p,
+                      I.tail_gather_d.p, tb);
+      }
+      const T* tx;
+      {
+        CommSerialScope serial;
+        tx = I.tail->cycle<T>(I.tailM);
+      }
+      if (L.n_cols) SHAKTI_LAUNCH((amg_gather_map_kernel<T>), div_up(L.n_cols, 256), 256, 0, s, L.n_cols, I.tail_gid.p, tx, v.x.p);
+      break;
+    }
     if (L.last) {
       if (I.dense_coarse) {
         const int32_t N = I.cN, nmax = std::max(I.cnmax, 1);
@@ -1129,7 +1333,7 @@ static void vcycle(Amg::Impl& I, const DevSell& Afine) {
           SHAKTI_CUDA(cudaMemsetAsync(I.crhs.p, 0, sizeof(double) * nmax, s));
           if (L.n) SHAKTI_LAUNCH((amg_convert_kernel<T, double>), div_up(L.n, 256), 256, 0, s, L.n, v.b.p, I.crhs.p);
           comm_allgather(I.crhs.p, I.cgather.p, nmax, s);
-          SHAKTI_LAUNCH(amg_compact_kernel, div_up(N, 128), 128, 0, s, N, nmax, comm().nranks, I.coff.p, I.cgather.p, I.cglob.p);
+          SHAKTI_LAUNCH((amg_compact_kernel<double>), div_up(N, 128), 128, 0, s, N, nmax, comm().nranks, I.coff.p, I.cgather.p, I.cglob.p);
           SHAKTI_LAUNCH((amg_dense_apply_kernel<double, double>), div_up((int64_t)N * 32, 128), 128, 0, s, N, I.dense.p, I.cglob.p, I.csol.p);
           if (L.n) SHAKTI_LAUNCH((amg_convert_kernel<double, T>), div_up(L.n, 256), 256, 0, s, L.n, I.csol.p + I.coff_me, v.x.p);
         } else if (L.n) {
@@ -1150,7 +1354,7 @@ static void vcycle(Amg::Impl& I, const DevSell& Afine) {
     CycleVecs<T>& v = vecs<T>(L);
     const DevSell& A = (l == 0) ? Afine : L.A;
     AmgLevel& C = *I.lv[l + 1];
-    C.halo->exchange(vecs<T>(C).x.p, s);
+    if (l + 1 != I.tail_level) C.halo->exchange(vecs<T>(C).x.p, s);   // the replicated level's ghosts are already set
     // own rows AND ghost rows of P are applied: the ghost part of x stays consistent with its owner
     // (it was exchanged before the residual), so the first post-smoothing step needs no exchange
     launch_spmv_add<T>(view_as<T>(L.P), vecs<T>(C).x.p, v.x.p, s);
@@ -1205,6 +1409,16 @@ static void run_cycle(Amg::Impl& I, const DevSell& Afine) {
   SHAKTI_CUDA(cudaGraphLaunch(I.gexec, s));
   g_kernel_launches += I.graph_launches;
 }
+
+template <class T> T* Amg::rhs_buffer() { return vecs<T>(*p_->lv[0]).b.p; }
+template <class T> const T* Amg::cycle(const DevSell& Afine) {
+  run_cycle<T>(*p_, Afine);
+  return static_cast<const T*>(p_->result_ptr);
+}
+template float* Amg::rhs_buffer<float>();
+template double* Amg::rhs_buffer<double>();
+template const float* Amg::cycle<float>(const DevSell&);
+template const double* Amg::cycle<double>(const DevSell&);
 
 void Amg::apply(const DevSell& Afine, const double* rin, double* z) {
   Impl& I = *p_;

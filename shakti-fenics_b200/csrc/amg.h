@@ -25,6 +25,8 @@ struct AmgOptions {
   int cuda_graph = 1;           // 1: replay the V-cycle as a captured CUDA graph
   int smoother_halo = 1;        // 1: halo exchange before every smoothing step; 0: only before residual / prolongation
                                 //    (ghost values lag one step inside the smoother: hybrid smoothing, fewer messages)
+  int replicate_below = 100000; // multi-GPU: the first level with at most this many rows in total (and everything below
+                                //    it) is replicated on every rank and solved there without communication
 };
 
 class Amg {
@@ -49,6 +51,12 @@ class Amg {
   // z = M^-1 r : one V-cycle from a zero initial guess.  r: n rows; z: n_cols-long buffer
   // (entries beyond n rows are left untouched and must be zero / halo-free).
   void apply(const DevSell& Afine, const double* r, double* z);
+  // The cycle in its own precision T (float for the mixed-precision cycle): right-hand side buffer of the
+  // fine level (n rows) and one V-cycle on it; returns the solution vector.  Used for the replicated
+  // coarse part of a distributed hierarchy.
+  template <class T> T* rhs_buffer();
+  template <class T> const T* cycle(const DevSell& Afine);
+  bool fp32() const;
   int levels() const;
   double operator_complexity() const;
   int64_t refreshes() const { return refreshes_; }

@@ -696,21 +696,54 @@ void launch_update_q_melt(int32_t n_owned, const int32_t* win, const double* x, 
 // ordered, neighbours are close in memory).
 enum { SPMV_SET = 0, SPMV_ADD = 1, SPMV_RESID = 2, SPMV_JACOBI = 3 };
 
-template <int MODE, class T>
+// KG = 1: one thread per row (large matrices: enough rows to fill the GPU, loads of a warp coalesce over
+// the 32 rows of a slice).  KG = 8: one 256-thread block per slice, warp g takes the entries k = g, g+8, ...
+// of all 32 rows (still coalesced) and the eight partial sums meet in shared memory.  That is for the small,
+// wide-rowed coarse levels of the AMG hierarchy, where one thread per row is a chain of ~100 dependent
+// gathers (15 us for a 500-row level) and the eight-way split cuts the chain eightfold.
+template <class T, int KG>
+__device__ __forceinline__ bool sell_row_dot(const SellViewT<T>& A, const T* __restrict__ x, int32_t& row, T& acc) {
+  if (KG == 1) {
+    row = blockIdx.x * blockDim.x + threadIdx.x;
+    const int32_t slice = row >> 5;
+    if (slice >= A.n_slices) return false;
+    const int32_t base = A.slice_ptr[slice];
+    const int32_t w = (A.slice_ptr[slice + 1] - base) >> 5;
+    const int32_t* __restrict__ cp = A.col + base + (row & 31);
+    const T* __restrict__ vp = A.val + base + (row & 31);
+    acc = 0;
+#pragma unroll 4
+    for (int k = 0; k < w; ++k) acc += vp[32 * k] * x[cp[32 * k]];
+    return row < A.n_rows;
+  } else {
+    __shared__ T psum[KG][32];
+    const int32_t slice = blockIdx.x;
+    const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+    row = slice * 32 + lane;
+    const int32_t base = A.slice_ptr[slice];
+    const int32_t w = (A.slice_ptr[slice + 1] - base) >> 5;
+    const int32_t* __restrict__ cp = A.col + base + lane;
+    const T* __restrict__ vp = A.val + base + lane;
+    T a = 0;
+    for (int k = g; k < w; k += KG) a += vp[32 * k] * x[cp[32 * k]];
+    psum[g][lane] = a;
+    __syncthreads();
+    if (g != 0) return false;
+#pragma unroll
+    for (int j = 1; j < KG; ++j) a += psum[j][lane];
+    acc = a;
+    return row < A.n_rows;
+  }
+}
+constexpr int32_t kWideRowsBelow = 300000;   // matrices with fewer rows use the KG = 8 kernels
+
+template <int MODE, class T, int KG>
 __global__ void __launch_bounds__(256)
 spmv_sell_kernel(SellViewT<T> A, const T* __restrict__ x, const T* __restrict__ b, const T* __restrict__ dinv, T omega,
                  T* __restrict__ y) {
-  const int32_t row = blockIdx.x * blockDim.x + threadIdx.x;
-  const int32_t slice = row >> 5;
-  if (slice >= A.n_slices) return;
-  const int32_t base = A.slice_ptr[slice];
-  const int32_t w = (A.slice_ptr[slice + 1] - base) >> 5;
-  const int32_t* __restrict__ cp = A.col + base + (row & 31);
-  const T* __restrict__ vp = A.val + base + (row & 31);
-  T acc = 0;
-#pragma unroll 4
-  for (int k = 0; k < w; ++k) acc += vp[32 * k] * x[cp[32 * k]];
-  if (row >= A.n_rows) return;
+  int32_t row;
+  T acc;
+  if (!sell_row_dot<T, KG>(A, x, row, acc)) return;
   if (MODE == SPMV_SET) y[row] = acc;
   else if (MODE == SPMV_ADD) y[row] += acc;
   else if (MODE == SPMV_RESID) y[row] = b[row] - acc;
@@ -720,8 +753,12 @@ spmv_sell_kernel(SellViewT<T> A, const T* __restrict__ x, const T* __restrict__ 
 template <int MODE, class T>
 static void spmv_launch(SellViewT<T> A, const T* x, const T* b, const T* dinv, double omega, T* y, cudaStream_t s) {
   if (A.n_rows == 0) return;
+  if (A.n_rows < kWideRowsBelow) {
+    SHAKTI_LAUNCH((spmv_sell_kernel<MODE, T, 8>), A.n_slices, 256, 0, s, A, x, b, dinv, (T)omega, y);
+    return;
+  }
   const int64_t threads = (int64_t)A.n_slices * 32;
-  SHAKTI_LAUNCH((spmv_sell_kernel<MODE, T>), div_up(threads, 256), 256, 0, s, A, x, b, dinv, (T)omega, y);
+  SHAKTI_LAUNCH((spmv_sell_kernel<MODE, T, 1>), div_up(threads, 256), 256, 0, s, A, x, b, dinv, (T)omega, y);
 }
 template <class T> void launch_spmv(SellViewT<T> A, const T* x, T* y, cudaStream_t s) { spmv_launch<SPMV_SET, T>(A, x, nullptr, nullptr, 0, y, s); }
 template <class T> void launch_spmv_add(SellViewT<T> A, const T* x, T* y, cudaStream_t s) { spmv_launch<SPMV_ADD, T>(A, x, nullptr, nullptr, 0, y, s); }

@@ -50,7 +50,7 @@ class Options(C.Structure):
         ("amg_smoother", C.c_int32), ("amg_fp32_cycle", C.c_int32),
         ("amg_cuda_graph", C.c_int32), ("amg_smoother_halo", C.c_int32),
         ("b_min", C.c_double), ("assembly_kernel", C.c_int32), ("reorder", C.c_int32),
-        ("linear_forcing", C.c_double),
+        ("linear_forcing", C.c_double), ("amg_replicate_below", C.c_int32),
     ]
 
 

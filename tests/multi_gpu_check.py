@@ -34,9 +34,21 @@ def main():
         return t.cpu().numpy()
 
     ok = True
-    for pc in ("jacobi", "amg"):
-        c = make_case(nx=48, ny=32, seed=9)
-        m = make_model(*c, device=local, precond=pc, linear_max_it=5000)
+    # (label, mesh, model options): the AMG runs cover the three shapes of a distributed hierarchy --
+    # everything replicated (tiny problem), distributed fine level + replicated rest, and several
+    # distributed levels with the replicated part starting where coarsening ends
+    runs = [("jacobi", (48, 32), dict(precond="jacobi")),
+            ("amg/replicated", (48, 32), dict(precond="amg")),
+            ("amg/fine-distributed", (48, 32), dict(precond="amg", amg_replicate_below=400)),
+            ("amg/3-level-distributed", (160, 120), dict(precond="amg", amg_replicate_below=0, amg_coarse_size=64)),
+            ("amg/no-graph", (96, 64), dict(precond="amg", amg_replicate_below=300, amg_cuda_graph=0)),
+            ("amg/bicgstab", (96, 64), dict(precond="amg", amg_replicate_below=300, linear_solver="bicgstab"))]
+    only = os.environ.get("SHAKTI_MG_ONLY")
+    for label, (nx, ny), opt in runs:
+        if only and only not in label:
+            continue
+        c = make_case(nx=nx, ny=ny, seed=9)
+        m = make_model(*c, device=local, linear_max_it=5000, **opt)
         st = m.stats()
         assert st["n_owned"] < st["n_vert"] and st["n_local"] > st["n_owned"], st
         F, J = m.assemble(3600.0)
@@ -45,6 +57,7 @@ def main():
         its = list(m.run(dts))
         fields = {k: gsum(m.get_field(k)) for k in ("N", "b", "melt_n", "N_n")}
         q = gsum(m.get_flux())
+        st = m.stats()
         if rank == 0:
             o = make_oracle(*c)
             Fo, Jo = o.assemble(3600.0)
@@ -54,8 +67,9 @@ def main():
             good = errs["F"] < 1e-12 and errs["J"] < 1e-12 and all(errs[k] < 1e-8 for k in ("N", "b", "melt", "q", "N_n")) \
                 and its == its_o
             ok &= good
-            print(f"[{world} GPUs, {pc}] newton {its} (oracle {its_o}) krylov {m.stats()['linear_its']} errs "
-                  + " ".join(f"{k}={v:.1e}" for k, v in errs.items()) + ("  OK" if good else "  MISMATCH"), flush=True)
+            print(f"[{world} GPUs, {label}, {nx}x{ny}] newton {its} (oracle {its_o}) krylov {st['linear_its']} amg levels "
+                  f"{st['amg_levels']} errs " + " ".join(f"{k}={v:.1e}" for k, v in errs.items())
+                  + ("  OK" if good else "  MISMATCH"), flush=True)
         m.close()
     capi.comm_finalize()
     dist.destroy_process_group()
