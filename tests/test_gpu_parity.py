@@ -291,9 +291,11 @@ def test_non_default_params_reach_every_kernel(name):
         for k, ref in (("N", o.N), ("b", o.b), ("melt_n", o.melt_n)):
             assert relinf(m.get_field(k), ref) < 1e-8, k
         assert relinf(m.get_flux(), o.q) < 1e-8
-        # nodal updates alone, from identical state
+        # nodal updates alone, from identical state (the transient fields agree to ~1e-10 only)
         o.N = o.N * 1.01
-        m.set_field("N", o.N)
+        for k, v in (("N", o.N), ("b", o.b), ("melt_n", o.melt_n)):
+            m.set_field(k, v)
+        m.set_flux(o.q)
         o.update_q(); o.update_melt(); o.update_b(DT)
         m.update_q(); m.update_melt(); m.update_b(DT)
         assert relinf(m.get_flux(), o.q) < 1e-12
