@@ -1231,11 +1231,11 @@ void Amg::refresh(const DevSell& Afine, const int32_t* fine_diag_pos) {
   I.graph_valid = false;
   if (!I.built) { build_hierarchy(I, Afine, fine_diag_pos); I.warm = false; }
   else {
-    for (size_t l = 0; l < I.lv.size(); ++l) numeric_level(I, l, Afine, fine_diag_pos);
-    refresh_tail(I, Afine);
+    { SHAKTI_PHASE("rf_numeric", s); for (size_t l = 0; l < I.lv.size(); ++l) numeric_level(I, l, Afine, fine_diag_pos); }
+    { SHAKTI_PHASE("rf_tail", s); refresh_tail(I, Afine); }
   }
-  update_smoother_bounds(I, Afine);
-  for (size_t l = 0; l < I.lv.size(); ++l) sync_cycle_precision(I, l, Afine, true);
+  { SHAKTI_PHASE("rf_bounds", s); update_smoother_bounds(I, Afine); }
+  { SHAKTI_PHASE("rf_f32", s); for (size_t l = 0; l < I.lv.size(); ++l) sync_cycle_precision(I, l, Afine, true); }
   if (I.dense_coarse) {
     AmgLevel& L = *I.lv.back();
     const DevSell& A = (I.lv.size() == 1) ? Afine : L.A;

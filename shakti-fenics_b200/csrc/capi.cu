@@ -174,6 +174,7 @@ static void ensure_rules(shakti_model* m) {
 }
 
 static void compute_kbar(shakti_model* m) {
+  SHAKTI_PHASE("kbar", m->stream);
   ensure_rules(m);
   launch_kbar(m->hm.ne, m->c0.p, m->c1.p, m->c2.p, m->x.p, m->y.p, m->b.p, m->qx.p, m->qy.p, m->kbar.p,
               m->dprm, m->stream);
@@ -181,6 +182,7 @@ static void compute_kbar(shakti_model* m) {
 
 // residual (+ Jacobian) at the current state; Kbar must be current
 static void assemble(shakti_model* m, double dt, int want_J) {
+  SHAKTI_PHASE(want_J ? "assembleFJ" : "assembleF", m->stream);
   refresh_h0(m);
   ensure_rules(m);
   const int32_t no = m->hm.n_owned;
@@ -232,11 +234,13 @@ static KrylovResult linear_solve(shakti_model* m, const double* rhs, double* dx,
   const int32_t no = m->hm.n_owned;
   SellView Jv = view(m->J);
   ApplyFn A = [m, Jv](double* xl, double* y) {
+    SHAKTI_PHASE("halo+spmv", m->stream);
     m->halo.exchange(xl, m->stream);
     launch_spmv(Jv, xl, y, m->stream);
   };
   AllReduceFn ar = [m](double* d, int c) { allreduce(m, d, c); };
   auto krylov = [&](const PrecFn& M, int max_it) {
+    SHAKTI_PHASE("krylov_total", m->stream);
     if (m->opt.linear_solver == SHAKTI_KSP_BICGSTAB) {
       if (!m->bicg_init) { m->bicg.init(no, m->hm.n_local, m->sm_count, m->stream); m->bicg_init = true; }
       return m->bicg.solve(A, M, ar, rhs, dx, rtol, m->opt.linear_atol, max_it);
@@ -258,6 +262,7 @@ static KrylovResult linear_solve(shakti_model* m, const double* rhs, double* dx,
     const double decades = std::max(1.0, -std::log10(std::max(rtol, 1e-300)));
     const bool degraded = m->rate_after_refresh > 0 && m->last_rate > 1.5 * m->rate_after_refresh + 0.25;
     auto do_refresh = [&]() {
+      SHAKTI_PHASE("amg_refresh", m->stream);
       m->amg->refresh(m->J, m->diag_pos.p);
       m->st.amg_refreshes++;
       m->step_of_refresh = m->st.steps;
@@ -265,8 +270,8 @@ static KrylovResult linear_solve(shakti_model* m, const double* rhs, double* dx,
     };
     bool fresh = false;
     if (!m->amg->ready() || due || degraded) { do_refresh(); fresh = true; }
-    else m->amg->refresh_fine_smoother(m->J, m->diag_pos.p);
-    PrecFn M = [m](const double* rr, double* z) { m->amg->apply(m->J, rr, z); };
+    else { SHAKTI_PHASE("amg_fine_smoother", m->stream); m->amg->refresh_fine_smoother(m->J, m->diag_pos.p); }
+    PrecFn M = [m](const double* rr, double* z) { SHAKTI_PHASE("vcycle", m->stream); m->amg->apply(m->J, rr, z); };
     int budget = m->opt.linear_max_it;
     if (!fresh && m->rate_after_refresh > 0) budget = std::min(budget, (int)(3.0 * m->rate_after_refresh * decades) + 20);
     r = krylov(M, budget);
@@ -418,6 +423,7 @@ static void update_melt(shakti_model* m) {
 }
 // q and melt_n in one pass (what shakti_step uses; identical results to update_q + update_melt)
 static void update_q_melt(shakti_model* m) {
+  SHAKTI_PHASE("nodal_q_melt", m->stream);
   refresh_h0(m);
   launch_update_q_melt(m->hm.n_owned, m->win.p, m->x.p, m->y.p, m->h0.p, m->N.p, m->b.p, m->qx.p, m->qy.p, m->G.p,
                        m->melt.p, m->melt2.p, m->dprm, m->stream);
@@ -425,6 +431,7 @@ static void update_q_melt(shakti_model* m) {
   m->halo.exchange(m->melt.p, m->stream);
 }
 static void update_b(shakti_model* m, double dt) {
+  SHAKTI_PHASE("nodal_b", m->stream);
   refresh_h0(m);
   launch_update_b(m->hm.n_owned, m->win.p, m->x.p, m->y.p, m->h0.p, m->N.p, m->b.p, m->qx.p, m->qy.p, m->G.p,
                   m->melt.p, m->b2.p, dt, m->opt.b_min, m->dprm, m->stream);
@@ -443,10 +450,14 @@ static void copy_N(shakti_model* m) {
 static void step(shakti_model* m, double dt, int32_t* niter, int32_t* converged) {
   SHAKTI_REQUIRE(dt > 0, "dt must be positive");
   int32_t it = 0, cv = 0;
-  newton_solve(m, dt, &it, &cv);
-  update_q_melt(m);
-  update_b(m, dt);
-  copy_N(m);
+  {
+    SHAKTI_PHASE("step_total", m->stream);
+    newton_solve(m, dt, &it, &cv);
+    update_q_melt(m);
+    update_b(m, dt);
+    copy_N(m);
+  }
+  if (phase_trace_enabled() && comm().rank == 0) phase_report("step");
   if (niter) *niter = it;
   if (converged) *converged = cv;
 }

@@ -90,4 +90,20 @@ struct DevBuf {
 
 inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// Diagnostic phase timer (SHAKTI_TRACE_PHASES=1): synchronises the stream at both ends of a scope and
+// accumulates wall time per name; shakti_step prints and clears the table on rank 0.  Off by default
+// (no synchronisation, no cost).
+bool phase_trace_enabled();
+void phase_add(const char* name, double ms);
+void phase_report(const char* title);
+struct PhaseScope {
+  const char* name;
+  cudaStream_t s;
+  double t0 = 0.0;
+  bool on;
+  PhaseScope(const char* n, cudaStream_t st);
+  ~PhaseScope();
+};
+#define SHAKTI_PHASE(name, stream) ::shakti::PhaseScope phase_scope_##__LINE__(name, stream)
+
 }  // namespace shakti

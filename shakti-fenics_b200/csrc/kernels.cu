@@ -3,12 +3,48 @@
 // solvers.  All fp64 / int32, HBM-bandwidth bound by design (no tensor cores: nothing here is
 // a dense contraction).  Reference formulas: source/constitutive.py:6-31, source/solvers.py:35-45.
 #include <algorithm>
+#include <cstdlib>
+#include <ctime>
 
 #include "device.h"
 
 namespace shakti {
 
 int64_t g_kernel_launches = 0;
+
+// ---- diagnostic phase timer (common.h)
+static std::vector<std::pair<std::string, std::pair<double, int64_t>>> g_phases;
+bool phase_trace_enabled() {
+  static const bool on = getenv("SHAKTI_TRACE_PHASES") != nullptr;
+  return on;
+}
+static double now_ms() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+void phase_add(const char* name, double ms) {
+  for (auto& p : g_phases)
+    if (p.first == name) { p.second.first += ms; p.second.second++; return; }
+  g_phases.push_back({name, {ms, 1}});
+}
+void phase_report(const char* title) {
+  if (g_phases.empty()) return;
+  fprintf(stderr, "[phases] %s:", title);
+  for (auto& p : g_phases) fprintf(stderr, " %s=%.2fms/%lld", p.first.c_str(), p.second.first, (long long)p.second.second);
+  fprintf(stderr, "\n");
+  g_phases.clear();
+}
+PhaseScope::PhaseScope(const char* n, cudaStream_t st) : name(n), s(st), on(phase_trace_enabled()) {
+  if (!on) return;
+  cudaStreamSynchronize(s);
+  t0 = now_ms();
+}
+PhaseScope::~PhaseScope() {
+  if (!on) return;
+  cudaStreamSynchronize(s);
+  phase_add(name, now_ms() - t0);
+}
 
 DevParams make_dev_params(const shakti_params& p) {
   DevParams d;
