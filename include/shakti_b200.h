@@ -241,6 +241,12 @@ int shakti_free_pinned(void* p);
  * launch in milliseconds (CUDA events on that stream).  `which`: 0 = SpMV (fine Jacobian),
  * 1 = F+J assembly, 2 = Kbar, 3 = nodal updates (q, melt, b), 4 = dot, 5 = axpy. */
 int shakti_time_kernel(shakti_model* m, int which, int reps, double dt, double* ms_per_launch);
+/* One smoothing step of AMG level `level` (the V-cycle's dominant kernel: SELL SpMV fused with the Chebyshev
+ * recurrence, in the cycle's precision), timed the same way.  Returns the level's local rows and stored
+ * entries and the bytes per matrix value (4: mixed-precision cycle), from which the caller forms the
+ * algorithmic bytes (value_bytes + 4) * nnz + 7 * value_bytes * rows.  Needs a built hierarchy (run a step). */
+int shakti_time_amg_smoother(shakti_model* m, int level, int reps, double* ms_per_launch, int64_t* rows,
+                             int64_t* nnz, int32_t* value_bytes);
 /* Algorithmic bytes per launch of kernel `which` (SURVEY.md §8d formulas). */
 int shakti_kernel_bytes(shakti_model* m, int which, double* bytes);
 

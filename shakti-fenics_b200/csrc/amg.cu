@@ -1410,6 +1410,19 @@ static void run_cycle(Amg::Impl& I, const DevSell& Afine) {
   g_kernel_launches += I.graph_launches;
 }
 
+bool Amg::launch_level_smoother(int level, const DevSell& Afine, int64_t* rows, int64_t* nnz) {
+  Impl& I = *p_;
+  if (!I.built || level < 0 || level >= (int)I.lv.size()) return false;
+  AmgLevel& L = *I.lv[level];
+  const DevSell& A = (level == 0) ? Afine : L.A;
+  if (rows) *rows = L.n;
+  if (nnz) *nnz = A.nnz;
+  if (L.n == 0) return true;
+  if (I.opt.fp32_cycle) launch_cheby<float>(viewf(A), L.vf.dinv.p, L.vf.b.p, L.vf.x.p, L.vf.d.p, L.vf.x2.p, 0.3, 0.2, I.s);
+  else launch_cheby<double>(view(A), L.vd.dinv.p, L.vd.b.p, L.vd.x.p, L.vd.d.p, L.vd.x2.p, 0.3, 0.2, I.s);
+  return true;
+}
+
 template <class T> T* Amg::rhs_buffer() { return vecs<T>(*p_->lv[0]).b.p; }
 template <class T> const T* Amg::cycle(const DevSell& Afine) {
   run_cycle<T>(*p_, Afine);

@@ -1192,6 +1192,32 @@ int shakti_time_kernel(shakti_model* m, int which, int reps, double dt, double* 
   SHAKTI_CATCH
 }
 
+int shakti_time_amg_smoother(shakti_model* m, int level, int reps, double* ms_per_launch, int64_t* rows, int64_t* nnz,
+                             int32_t* value_bytes) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(m && ms_per_launch && reps > 0, "bad arguments");
+  use_device(m);
+  SHAKTI_REQUIRE(m->amg && m->amg->ready() && m->J_valid, "no AMG hierarchy yet: run a step first");
+  int64_t r = 0, z = 0;
+  SHAKTI_REQUIRE(m->amg->launch_level_smoother(level, m->J, &r, &z), "no such AMG level on this rank");
+  cudaEvent_t e0, e1;
+  SHAKTI_CUDA(cudaEventCreate(&e0));
+  SHAKTI_CUDA(cudaEventCreate(&e1));
+  SHAKTI_CUDA(cudaEventRecord(e0, m->stream));
+  for (int i = 0; i < reps; ++i) m->amg->launch_level_smoother(level, m->J, nullptr, nullptr);
+  SHAKTI_CUDA(cudaEventRecord(e1, m->stream));
+  SHAKTI_CUDA(cudaEventSynchronize(e1));
+  float ms = 0;
+  SHAKTI_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_per_launch = (double)ms / reps;
+  if (rows) *rows = r;
+  if (nnz) *nnz = z;
+  if (value_bytes) *value_bytes = m->amg->fp32() ? 4 : 8;
+  SHAKTI_CATCH
+}
+
 int shakti_comm_unique_id(uint8_t id[128]) {
   SHAKTI_TRY
   comm_unique_id(id);

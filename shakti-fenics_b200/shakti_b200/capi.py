@@ -447,6 +447,14 @@ class Model:
         _check(self.lib.shakti_time_kernel(self._h, C.c_int(self.KERNELS[which]), C.c_int(reps), C.c_double(dt), C.byref(ms)))
         return ms.value
 
+    def time_amg_smoother(self, level, reps=20):
+        """-> dict(ms, rows, nnz, value_bytes, bytes) for one smoothing step of AMG level `level`."""
+        ms, rows, nnz, vb = C.c_double(0), C.c_int64(0), C.c_int64(0), C.c_int32(0)
+        _check(self.lib.shakti_time_amg_smoother(self._h, C.c_int(level), C.c_int(reps), C.byref(ms), C.byref(rows),
+                                                 C.byref(nnz), C.byref(vb)))
+        by = (vb.value + 4) * nnz.value + 7 * vb.value * rows.value
+        return dict(ms=ms.value, rows=rows.value, nnz=nnz.value, value_bytes=vb.value, bytes=by)
+
     def kernel_bytes(self, which):
         b = C.c_double(0)
         _check(self.lib.shakti_kernel_bytes(self._h, C.c_int(self.KERNELS[which]), C.byref(b)))
