@@ -177,6 +177,68 @@ struct ElemOut {
   double J[3][3];
 };
 
+// closure (A b N^3, its N-derivative) and lake-storage terms of one cell by Radon's 7-point rule
+// (see element_core); ST = false leaves the storage part out (cells with no storage).
+template <bool ST>
+__device__ __forceinline__ void reaction_radon7(double detabs, const double bb[3], const double Nv[3], const double Nn[3],
+                                                const double st[3], double cs, double A, double& f0, double& f1, double& f2,
+                                                double& m00, double& m01, double& m02, double& m11, double& m12, double& m22) {
+  double dqv[3] = {0, 0, 0}, sv[3] = {0, 0, 0}, Sd = 0, Ss = 0;
+  if (ST) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { dqv[i] = Nv[i] - Nn[i]; sv[i] = st[i] * cs; }
+    Sd = dqv[0] + dqv[1] + dqv[2];
+    Ss = sv[0] + sv[1] + sv[2];
+  }
+  const double Sb = bb[0] + bb[1] + bb[2], SN = Nv[0] + Nv[1] + Nv[2];
+  const double A3 = 3.0 * A;
+  {  // centroid, weight 9/80
+    const double w = 0.1125 * detabs, t = 1.0 / 3.0;
+    const double bq = Sb * t, Nq = SN * t, N2 = Nq * Nq;
+    double r = A * bq * Nq * N2, d = A3 * bq * N2;
+    if (ST) {
+      const double dq = Sd * t, sq = Ss * t;
+      r += sq * dq;
+      d += sq;
+    }
+    r *= w * t;
+    d *= w * (t * t);
+    f0 = f1 = f2 = r;
+    m00 = m01 = m02 = m11 = m12 = m22 = d;
+  }
+  const double s15 = 3.872983346207417;   // sqrt(15)
+#pragma unroll
+  for (int orb = 0; orb < 2; ++orb) {
+    const double a = orb == 0 ? (6.0 - s15) / 21.0 : (6.0 + s15) / 21.0;
+    const double w = (orb == 0 ? (155.0 - s15) : (155.0 + s15)) * (1.0 / 2400.0) * detabs;
+    const double e = 1.0 - 3.0 * a;   // c - a
+    const double ab = a * Sb, aN = a * SN, ad = a * Sd, as = a * Ss;
+    double r[3], d[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const double bq = ab + e * bb[i], Nq = aN + e * Nv[i];
+      const double N2 = Nq * Nq;
+      double ri = A * bq * Nq * N2, di = A3 * bq * N2;
+      if (ST) {
+        const double dq = ad + e * dqv[i], sq = as + e * sv[i];
+        ri += sq * dq;
+        di += sq;
+      }
+      r[i] = w * ri;
+      d[i] = w * di;
+    }
+    const double R = a * (r[0] + r[1] + r[2]), D = a * a * (d[0] + d[1] + d[2]);
+    const double ae = a * e, ee = e * e;
+    f0 += R + e * r[0]; f1 += R + e * r[1]; f2 += R + e * r[2];
+    m00 += D + (2.0 * ae + ee) * d[0];
+    m11 += D + (2.0 * ae + ee) * d[1];
+    m22 += D + (2.0 * ae + ee) * d[2];
+    m01 += D + ae * (d[0] + d[1]);
+    m02 += D + ae * (d[0] + d[2]);
+    m12 += D + ae * (d[1] + d[2]);
+  }
+}
+
 __device__ __forceinline__ void element_core(const Geo& g, const double h[3], const double bb[3], const double mm[3],
                                              const double qxv[3], const double qyv[3], const double Nv[3],
                                              const double Nn[3], const double st[3], const double Gv[3],
@@ -221,44 +283,12 @@ __device__ __forceinline__ void element_core(const Geo& g, const double h[3], co
     // A P1 function with nodal values f_i and sum S is  S/3 at the centroid and  a S + (c-a) f_i  at
     // orbit point i (barycentrics (a,a,c) permuted), so every interpolation is one FMA; the
     // phi_a, phi_a phi_b weights collapse to  a R + e r_a  and  a^2 D + a e (d_a + d_b) + e^2 delta_ab d_a.
-    const double dqv[3] = {Nv[0] - Nn[0], Nv[1] - Nn[1], Nv[2] - Nn[2]};
-    const double sv[3] = {st[0] * cs, st[1] * cs, st[2] * cs};
-    const double Sb = bb[0] + bb[1] + bb[2], SN = Nv[0] + Nv[1] + Nv[2], Sd = dqv[0] + dqv[1] + dqv[2],
-                 Ss = sv[0] + sv[1] + sv[2];
-    const double A3 = 3.0 * p.A;
-    {  // centroid, weight 9/80
-      const double w = 0.1125 * g.detabs, t = 1.0 / 3.0;
-      const double bq = Sb * t, Nq = SN * t, dq = Sd * t, sq = Ss * t, N2 = Nq * Nq;
-      const double r = w * (p.A * bq * Nq * N2 + sq * dq) * t;
-      const double d = w * (A3 * bq * N2 + sq) * (t * t);
-      f0 = f1 = f2 = r;
-      m00 = m01 = m02 = m11 = m12 = m22 = d;
-    }
-    const double s15 = 3.872983346207417;   // sqrt(15)
-#pragma unroll
-    for (int orb = 0; orb < 2; ++orb) {
-      const double a = orb == 0 ? (6.0 - s15) / 21.0 : (6.0 + s15) / 21.0;
-      const double w = (orb == 0 ? (155.0 - s15) : (155.0 + s15)) * (1.0 / 2400.0) * g.detabs;
-      const double e = 1.0 - 3.0 * a;   // c - a
-      const double ab = a * Sb, aN = a * SN, ad = a * Sd, as = a * Ss;
-      double r[3], d[3];
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const double bq = ab + e * bb[i], Nq = aN + e * Nv[i], dq = ad + e * dqv[i], sq = as + e * sv[i];
-        const double N2 = Nq * Nq;
-        r[i] = w * (p.A * bq * Nq * N2 + sq * dq);
-        d[i] = w * (A3 * bq * N2 + sq);
-      }
-      const double R = a * (r[0] + r[1] + r[2]), D = a * a * (d[0] + d[1] + d[2]);
-      const double ae = a * e, ee = e * e;
-      f0 += R + e * r[0]; f1 += R + e * r[1]; f2 += R + e * r[2];
-      m00 += D + (2.0 * ae + ee) * d[0];
-      m11 += D + (2.0 * ae + ee) * d[1];
-      m22 += D + (2.0 * ae + ee) * d[2];
-      m01 += D + ae * (d[0] + d[1]);
-      m02 += D + ae * (d[0] + d[2]);
-      m12 += D + ae * (d[1] + d[2]);
-    }
+    // Cells outside the lakes (storage == 0 at all three vertices: almost all of them) skip the storage
+    // interpolations; the branch is uniform over long runs of cells.
+    if (st[0] != 0.0 || st[1] != 0.0 || st[2] != 0.0)
+      reaction_radon7<true>(g.detabs, bb, Nv, Nn, st, cs, p.A, f0, f1, f2, m00, m01, m02, m11, m12, m22);
+    else
+      reaction_radon7<false>(g.detabs, bb, Nv, Nn, st, cs, p.A, f0, f1, f2, m00, m01, m02, m11, m12, m22);
   } else {
     // general Glen exponent: the closure is not polynomial; use the table in __constant__ memory
     const double e1 = p.n - 1.0, e2 = p.n - 2.0;
@@ -526,14 +556,238 @@ assemble_blocks_kernel(int32_t n_owned, int32_t rows_per_block, int32_t cap, int
   }
 }
 
+// ---- version 2 of the row-block kernel (default).  Same algorithm and same plan; what changed, guided by the
+// round-1 ncu capture (issue/latency bound at 24 % occupancy, IMAD+ISETP over half of the stall samples):
+//   * CAP / VCAP are template constants: every shared-memory address is base + immediate, the runtime
+//     multiplications (IMAD) of the 36 vertex loads and 12 stores per cell disappear;
+//   * phase 0 stages the block's OWN rows -- twelve contiguous 1 KB slices -- with the bulk asynchronous copy
+//     engine (cp.async.bulk global -> shared, completion on an mbarrier: SASS UBLKCP), issued by one thread
+//     while the others gather the few halo vertices and prefetch the cell metadata;
+//   * the head is formed per cell from the staged h0 and N (3 FMAs) instead of in the staging pass;
+//   * cells without lake storage (all of them outside the lakes) skip the storage part of the quadrature.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+enum { WX = 0, WY, WH0, WN, WNN, WB, WQX, WQY, WG, WM, WS, WI, WFIELDS };
+
+template <int VCAP>
+__device__ __forceinline__ void element_FJ_staged2(const int v[3], const double* __restrict__ sV, double kb, double dt,
+                                                   const DevParams& p, ElemOut& o, double Nv[3]) {
+  const Geo g = geometry(sV[WX * VCAP + v[0]], sV[WY * VCAP + v[0]], sV[WX * VCAP + v[1]], sV[WY * VCAP + v[1]],
+                         sV[WX * VCAP + v[2]], sV[WY * VCAP + v[2]]);
+  double h[3], bb[3], mm[3], qxv[3], qyv[3], Nn[3], st[3], Gv[3], inp[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    Nv[i] = sV[WN * VCAP + v[i]];
+    h[i] = sV[WH0 * VCAP + v[i]] - Nv[i] * p.inv_rwg;   // Head (constitutive.py:6-9)
+    Nn[i] = sV[WNN * VCAP + v[i]];
+    bb[i] = sV[WB * VCAP + v[i]];
+    qxv[i] = sV[WQX * VCAP + v[i]];
+    qyv[i] = sV[WQY * VCAP + v[i]];
+    Gv[i] = sV[WG * VCAP + v[i]];
+    mm[i] = sV[WM * VCAP + v[i]];
+    st[i] = sV[WS * VCAP + v[i]];
+    inp[i] = sV[WI * VCAP + v[i]];
+  }
+  element_core(g, h, bb, mm, qxv, qyv, Nv, Nn, st, Gv, inp, kb, dt, p, o);
+}
+
+template <int CAP, int VCAP>
+__global__ void __launch_bounds__(128, 4)
+assemble_blocks_v2_kernel(int32_t n_owned, int32_t rows_per_block, const int32_t* __restrict__ blk_eptr,
+                          const int32_t* __restrict__ blk_elems, const uint16_t* __restrict__ blk_lv,
+                          const int32_t* __restrict__ blk_hptr, const int32_t* __restrict__ blk_halo,
+                          const int32_t* __restrict__ inc_ptr, const uint16_t* __restrict__ inc_code,
+                          const uint32_t* __restrict__ src, FieldPtrs f, const double* __restrict__ kbar, double dt,
+                          double N_bdry, const int32_t* __restrict__ slice_ptr, double* __restrict__ F,
+                          double* __restrict__ Jval, int want_J, DevParams p) {
+  extern __shared__ __align__(16) double smem[];
+  double* sV = smem;                               // [WFIELDS][VCAP]
+  double* sK = smem + (size_t)WFIELDS * VCAP;      // [12][CAP]: F0..F2, J00..J22
+  uint8_t* sBC = reinterpret_cast<uint8_t*>(sK + (size_t)12 * CAP);   // [VCAP]
+  __shared__ __align__(8) uint64_t bar;
+  const int32_t r0 = blockIdx.x * rows_per_block;
+  const int32_t nrows = min(rows_per_block, n_owned - r0);
+  const int32_t h0 = blk_hptr[blockIdx.x], nh = blk_hptr[blockIdx.x + 1] - h0;
+  const double* const fld[WFIELDS] = {f.x, f.y, f.h0, f.N, f.N_n, f.b, f.qx, f.qy, f.G, f.melt, f.storage, f.inputs};
+  // ---- phase 0a: own rows by bulk copy (whole blocks only: sizes must be multiples of 16 bytes)
+  const bool bulk = (nrows == rows_per_block) && ((rows_per_block & 1) == 0);
+  if (bulk && threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    mbar_expect_tx(&bar, (uint32_t)(WFIELDS * nrows * sizeof(double)));
+#pragma unroll
+    for (int k = 0; k < WFIELDS; ++k) bulk_g2s(sV + k * VCAP, fld[k] + r0, (uint32_t)(nrows * sizeof(double)), &bar);
+  }
+  // cell ids, Kbar and block-local vertex ids of this thread's cells are requested first: the chain
+  // blk_elems -> kbar would otherwise be exposed at the start of every cell
+  constexpr int kCellsPre = 4;
+  const int32_t e0 = blk_eptr[blockIdx.x], e1 = blk_eptr[blockIdx.x + 1];
+  double kb_pre[kCellsPre];
+  uint32_t lv01_pre[kCellsPre], lv2_pre[kCellsPre];
+#pragma unroll
+  for (int c = 0; c < kCellsPre; ++c) {
+    const int32_t le = threadIdx.x + c * blockDim.x;
+    kb_pre[c] = 0.0; lv01_pre[c] = 0; lv2_pre[c] = 0;
+    if (le < e1 - e0) {
+      const uint16_t* lv = blk_lv + 3 * (size_t)(e0 + le);
+      lv01_pre[c] = (uint32_t)lv[0] | ((uint32_t)lv[1] << 16);
+      lv2_pre[c] = lv[2];
+      kb_pre[c] = kbar[blk_elems[e0 + le]];
+    }
+  }
+  // ---- phase 0b: halo vertices (and everything, for the last partial block) by per-thread loads
+  for (int32_t i = (bulk ? nrows : 0) + threadIdx.x; i < nrows + nh; i += blockDim.x) {
+    const int32_t g = i < nrows ? r0 + i : blk_halo[h0 + i - nrows];
+#pragma unroll
+    for (int k = 0; k < WFIELDS; ++k) sV[k * VCAP + i] = fld[k][g];
+    sBC[i] = f.isbc[g];
+  }
+  if (bulk)
+    for (int32_t i = threadIdx.x; i < nrows; i += blockDim.x) sBC[i] = f.isbc[r0 + i];
+  __syncthreads();            // mbarrier initialised (thread 0) and the per-thread stores are visible
+  if (bulk) mbar_wait(&bar, 0);
+  // ---- phase 1
+#pragma unroll 1
+  for (int c = 0; c * (int32_t)blockDim.x + (int32_t)threadIdx.x < e1 - e0; ++c) {
+    const int32_t le = threadIdx.x + c * blockDim.x;
+    int v[3];
+    double kb;
+    if (c < kCellsPre) {
+      uint32_t a01 = lv01_pre[0], a2 = lv2_pre[0];
+      kb = kb_pre[0];
+#pragma unroll
+      for (int q = 1; q < kCellsPre; ++q)
+        if (c == q) { a01 = lv01_pre[q]; a2 = lv2_pre[q]; kb = kb_pre[q]; }
+      v[0] = a01 & 0xFFFFu; v[1] = a01 >> 16; v[2] = a2;
+    } else {
+      const uint16_t* lv = blk_lv + 3 * (size_t)(e0 + le);
+      v[0] = lv[0]; v[1] = lv[1]; v[2] = lv[2];
+      kb = kbar[blk_elems[e0 + le]];
+    }
+    ElemOut o;
+    double Nv[3];
+    element_FJ_staged2<VCAP>(v, sV, kb, dt, p, o, Nv);
+    const bool bc[3] = {sBC[v[0]] != 0, sBC[v[1]] != 0, sBC[v[2]] != 0};
+    apply_lifting(o, Nv, bc, N_bdry);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      sK[a * CAP + le] = o.F[a];
+#pragma unroll
+      for (int b = 0; b < 3; ++b) sK[(3 + 3 * a + b) * CAP + le] = (bc[a] || bc[b]) ? 0.0 : o.J[a][b];
+    }
+  }
+  // ---- phase 2 (first loads issued before the barrier, see the version above)
+  constexpr int kPre = 8;
+  const bool has_row = (int32_t)threadIdx.x < nrows;
+  const int32_t row = r0 + threadIdx.x;
+  int32_t base = 0, w = 0, ib = 0, ie = 0;
+  uint32_t pre[kPre];
+  if (has_row) {
+    const int32_t slice = row >> 5;
+    base = slice_ptr[slice];
+    w = (slice_ptr[slice + 1] - base) >> 5;
+    ib = inc_ptr[row];
+    ie = inc_ptr[row + 1];
+    if (want_J) {
+#pragma unroll
+      for (int k = 0; k < kPre; ++k) pre[k] = k < w ? src[base + 32 * k + (row & 31)] : 0xFFFFFFFFu;
+    }
+  }
+  __syncthreads();
+  if (!has_row) return;
+  const bool rbc = sBC[threadIdx.x] != 0;
+  double Fr = 0.0, Jd = 0.0;
+  for (int32_t k = ib; k < ie; ++k) {
+    const uint32_t code = inc_code[k];
+    const uint32_t le = code >> 2, a = code & 3u;
+    Fr += sK[a * CAP + le];
+    Jd += sK[(3 + 4 * a) * CAP + le];
+  }
+  F[row] = rbc ? sV[WN * VCAP + threadIdx.x] - N_bdry : Fr;
+  if (!want_J) return;
+  auto entry = [&](uint32_t s2, int32_t pos) {
+    if (s2 == 0xFFFFFFFFu) return;         // padding
+    double v;
+    if (s2 == 0xFFFEFFFEu) v = rbc ? 1.0 : Jd;
+    else {
+      const uint32_t ca = s2 & 0xFFFFu, cb = s2 >> 16;
+      v = sK[(3 + (ca & 15u)) * CAP + (ca >> 4)];
+      if (cb != 0xFFFFu) v += sK[(3 + (cb & 15u)) * CAP + (cb >> 4)];
+    }
+    Jval[pos] = v;
+  };
+#pragma unroll
+  for (int k = 0; k < kPre; ++k)
+    if (k < w) entry(pre[k], base + 32 * k + (row & 31));
+  for (int k = kPre; k < w; ++k) {
+    const int32_t pos = base + 32 * k + (row & 31);
+    entry(src[pos], pos);
+  }
+}
+
+template <int CAP, int VCAP>
+static void launch_assemble_blocks_v2(const AssemblyPlanView& pl, FieldPtrs f, const double* kbar, double dt, double N_bdry,
+                                      const int32_t* slice_ptr, double* F, double* Jval, int want_J, DevParams p, int dev,
+                                      cudaStream_t s) {
+  constexpr size_t smem = ((size_t)WFIELDS * VCAP + (size_t)12 * CAP) * sizeof(double) + VCAP;
+  static bool configured[64] = {};   // the opt-in is per device
+  if (!configured[dev & 63]) {
+    SHAKTI_CUDA(cudaFuncSetAttribute((assemble_blocks_v2_kernel<CAP, VCAP>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[dev & 63] = true;
+  }
+  SHAKTI_LAUNCH((assemble_blocks_v2_kernel<CAP, VCAP>), pl.n_blocks, 128, smem, s, pl.n_owned, pl.rows_per_block, pl.blk_eptr,
+                pl.blk_elems, pl.blk_lv, pl.blk_hptr, pl.blk_halo, pl.inc_ptr, pl.inc_code, pl.src, f, kbar, dt, N_bdry, slice_ptr, F,
+                Jval, want_J, p);
+}
+
 void launch_assemble_blocks(const AssemblyPlanView& pl, FieldPtrs f, const double* kbar, double dt, double N_bdry,
                             const int32_t* slice_ptr, double* F, double* Jval, int want_J, DevParams p, cudaStream_t s) {
   if (pl.n_blocks == 0) return;
+  int dev = 0;
+  SHAKTI_CUDA(cudaGetDevice(&dev));
+  static const bool use_v1 = getenv("SHAKTI_ASM_V1") != nullptr;   // A/B switch: the round-1 kernel
+  if (!use_v1 && pl.rows_per_block == 128) {
+    // compile-time capacities: (352, 226) keeps 4 blocks per SM (55.7 KB each) and covers Morton-ordered
+    // triangulations of structured-like density (C2-C5: at most 350 cells, 226 vertices per block);
+    // (400, 256) is the roomier instance (3 blocks per SM); anything larger runs the runtime-stride kernel
+    if (pl.cap <= 352 && pl.vcap <= 226) {
+      launch_assemble_blocks_v2<352, 226>(pl, f, kbar, dt, N_bdry, slice_ptr, F, Jval, want_J, p, dev, s);
+      return;
+    }
+    if (pl.cap <= 400 && pl.vcap <= 256) {
+      launch_assemble_blocks_v2<400, 256>(pl, f, kbar, dt, N_bdry, slice_ptr, F, Jval, want_J, p, dev, s);
+      return;
+    }
+  }
   const size_t smem = ((size_t)VFIELDS * pl.vcap + (size_t)12 * pl.cap) * sizeof(double) + pl.vcap;
-  static size_t configured = 0;
-  if (smem > configured) {
+  static size_t configured[64] = {};    // per device (a process may drive several GPUs)
+  if (smem > configured[dev & 63]) {
     SHAKTI_CUDA(cudaFuncSetAttribute(assemble_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+    configured[dev & 63] = smem;
   }
   const int threads = pl.rows_per_block >= 256 ? 256 : 128;   // phase 2 needs one thread per row
   SHAKTI_LAUNCH(assemble_blocks_kernel, pl.n_blocks, threads, smem, s, pl.n_owned, pl.rows_per_block, pl.cap, pl.vcap,
