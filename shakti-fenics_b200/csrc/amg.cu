@@ -668,7 +668,7 @@ void Amg::setup(const HostCsr& A0, const HostSell& S0, const std::vector<uint8_t
   I.tail.reset();
   I.tail_level = -1;
   I.scal.alloc_zero(4, s);
-  if (!I.host_scal) SHAKTI_CUDA(cudaMallocHost(&I.host_scal, 4 * sizeof(double)));
+  if (!I.host_scal) SHAKTI_CUDA(cudaMallocHost(&I.host_scal, 32 * sizeof(double)));
   refreshes_ = 0;
 }
 
@@ -751,8 +751,10 @@ static void update_smoother_bounds(Amg::Impl& I, const DevSell& Afine) {
   }
   comm_allreduce_max(I.lmax_dev.p, (int)nl, s);
   std::vector<double> h(nl);
-  SHAKTI_CUDA(cudaMemcpyAsync(h.data(), I.lmax_dev.p, sizeof(double) * nl, cudaMemcpyDeviceToHost, s));
+  SHAKTI_REQUIRE(nl <= 32, "AMG: more than 32 levels");
+  launch_readback(I.lmax_dev.p, I.host_scal, (int)nl, s);
   SHAKTI_CUDA(cudaStreamSynchronize(s));
+  for (size_t l = 0; l < nl; ++l) h[l] = I.host_scal[l];
   for (size_t l = 0; l < nl; ++l) I.lv[l]->lmax = (h[l] > 0 && std::isfinite(h[l])) ? h[l] : 2.0;
 }
 
@@ -1219,7 +1221,7 @@ void Amg::refresh_fine_smoother(const DevSell& Afine, const int32_t* fine_diag_p
     SHAKTI_LAUNCH(amg_gershgorin_kernel, div_up(L.n, 256), 256, 0, s, view(Afine), L.dinv.p,
                   reinterpret_cast<unsigned long long*>(I.scal.p + 1));
   comm_allreduce_max(I.scal.p + 1, 1, s);
-  SHAKTI_CUDA(cudaMemcpyAsync(I.host_scal, I.scal.p + 1, sizeof(double), cudaMemcpyDeviceToHost, s));
+  launch_readback(I.scal.p + 1, I.host_scal, 1, s);
   SHAKTI_CUDA(cudaStreamSynchronize(s));
   if (I.host_scal[0] > 0 && std::isfinite(I.host_scal[0])) L.lmax = I.host_scal[0];
   sync_cycle_precision(I, 0, Afine, false);

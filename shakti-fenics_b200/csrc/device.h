@@ -122,6 +122,12 @@ void launch_multi_axpy_neg_scale(int64_t n, int nvec, const double* V, int64_t l
 // y = sum_k h[k] V_k
 void launch_combine(int64_t n, int nvec, const double* V, int64_t ld, const double* h, double* y,
                     cudaStream_t s);
+// dst_host[0..count) = src[0..count): a KERNEL stores into page-locked host memory (cudaMallocHost memory is
+// device-accessible under unified addressing).  The small per-iteration reads of the solvers must not go
+// through the copy engines: while the asynchronous save path moves hundreds of MB to the host, an 8-byte
+// cudaMemcpyAsync would queue behind a 128 MB chunk (measured: 16 ms per step lost at C4).  The caller
+// synchronises the stream before reading.
+void launch_readback(const double* src, double* dst_host, int count, cudaStream_t s);
 void launch_axpy(int64_t n, double alpha, const double* x, double* y, cudaStream_t s);  // y += alpha x
 void launch_xmy_masked(int64_t n, const double* a, const uint8_t* mask, double* out, cudaStream_t s);
 void launch_pointwise_mul(int64_t n, const double* a, const double* b, double scale, double* out, cudaStream_t s);

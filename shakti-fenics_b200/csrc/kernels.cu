@@ -1335,6 +1335,15 @@ void launch_combine(int64_t n, int nvec, const double* V, int64_t ld, const doub
   }
 }
 
+__global__ void readback_kernel(const double* __restrict__ src, double* __restrict__ dst_host, int count) {
+  for (int i = threadIdx.x; i < count; i += blockDim.x) dst_host[i] = src[i];
+  __threadfence_system();
+}
+void launch_readback(const double* src, double* dst_host, int count, cudaStream_t s) {
+  if (count <= 0) return;
+  SHAKTI_LAUNCH(readback_kernel, 1, 64, 0, s, src, dst_host, count);
+}
+
 // ------------------------------------------------------------------ streaming vector kernels
 __global__ void axpy_kernel(int64_t n, double alpha, const double* __restrict__ x, double* __restrict__ y) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;

@@ -65,7 +65,7 @@ KrylovResult Gmres::solve(const ApplyFn& A, const PrecFn& M, const AllReduceFn& 
   double bnorm = -1.0, tol = 0.0;
   int total = 0;
   auto read = [&](const double* dev, int count) {
-    SHAKTI_CUDA(cudaMemcpyAsync(hbuf, dev, count * sizeof(double), cudaMemcpyDeviceToHost, s_));
+    launch_readback(dev, hbuf, count, s_);
     SHAKTI_CUDA(cudaStreamSynchronize(s_));
   };
   for (;;) {
@@ -178,7 +178,7 @@ KrylovResult BiCgStab::solve(const ApplyFn& A, const PrecFn& M, const AllReduceF
   auto dot = [&](const double* a, const double* c) {
     launch_multi_dot(red_, n_, 1, a, n_, c, dots_.p, s_);
     allreduce(dots_.p, 1);
-    SHAKTI_CUDA(cudaMemcpyAsync(host_, dots_.p, sizeof(double), cudaMemcpyDeviceToHost, s_));
+    launch_readback(dots_.p, host_, 1, s_);
     SHAKTI_CUDA(cudaStreamSynchronize(s_));
     return host_[0];
   };
