@@ -46,6 +46,7 @@ struct shakti_model {
   // vertex fields (n_local)
   DevBuf<double> z_b, z_s, h0, G, inputs, storage, b, b2, N, N_n, qx, qy, melt, melt2, F, dx, rhs, dinv;
   DevBuf<double> kbar;
+  DevBuf<double> kbar_blk;   // Kbar in the block order of the assembly plan (kbar[ab_elems[i]])
   DevBuf<uint8_t> isbc;
   DevBuf<double> stage;   // nv_g doubles: caller-numbered staging for set/get
   DevBuf<double> stage2;  // 2 nv_g (interleaved flux)
@@ -178,6 +179,8 @@ static void compute_kbar(shakti_model* m) {
   ensure_rules(m);
   launch_kbar(m->hm.ne, m->c0.p, m->c1.p, m->c2.p, m->x.p, m->y.p, m->b.p, m->qx.p, m->qy.p, m->kbar.p,
               m->dprm, m->stream);
+  // block-ordered copy for the row-block assembly: its cells then read Kbar without the cell-id indirection
+  if (m->kbar_blk.n) launch_gather((int64_t)m->kbar_blk.n, m->ab_elems.p, m->kbar.p, m->kbar_blk.p, m->stream);
 }
 
 // residual (+ Jacobian) at the current state; Kbar must be current
@@ -189,7 +192,7 @@ static void assemble(shakti_model* m, double dt, int want_J) {
   if (m->opt.assembly_kernel == 0 && m->ab.ok) {
     AssemblyPlanView pl{no, m->ab.rows_per_block, m->ab.n_blocks, m->ab.max_cells, m->ab.max_verts, m->ab_eptr.p,
                         m->ab_elems.p, m->ab_lv.p, m->ab_hptr.p, m->ab_halo.p, m->ab_incptr.p, m->ab_inc.p, m->ab_src.p};
-    launch_assemble_blocks(pl, m->fields(), m->kbar.p, dt, m->N_bdry, m->J.slice_ptr.p, m->F.p, m->J.val.p, want_J,
+    launch_assemble_blocks(pl, m->fields(), m->kbar.p, m->kbar_blk.n ? m->kbar_blk.p : nullptr, dt, m->N_bdry, m->J.slice_ptr.p, m->F.p, m->J.val.p, want_J,
                            m->dprm, m->stream);
     if (want_J) m->J_valid = true;
     return;
@@ -486,9 +489,15 @@ static void save_outputs_async(shakti_model* m, double* b_out, double* N_out, do
   }
   SHAKTI_CUDA(cudaEventRecord(m->ev_snap, m->stream));
   SHAKTI_CUDA(cudaStreamWaitEvent(m->copy_stream, m->ev_snap, 0));
+  // in chunks: the copy engine serves its queue in order, and a step's small reads (when they go through it)
+  // must not wait behind a whole 128 MB field
+  const char* ce = getenv("SHAKTI_D2H_CHUNK_MB");
+  const size_t chunk = (size_t)(ce ? std::max(1, atoi(ce)) : 8) << 17;   // doubles per chunk (MB * 2^20 / 8)
   for (int k = 0; k < 4; ++k)
     if (outs[k] && n_out)
-      SHAKTI_CUDA(cudaMemcpyAsync(outs[k], m->out_stage[k].p, sizeof(double) * n_out, cudaMemcpyDeviceToHost, m->copy_stream));
+      for (size_t o = 0; o < n_out; o += chunk)
+        SHAKTI_CUDA(cudaMemcpyAsync(outs[k] + o, m->out_stage[k].p + o, sizeof(double) * std::min(chunk, n_out - o),
+                                    cudaMemcpyDeviceToHost, m->copy_stream));
   SHAKTI_CUDA(cudaEventRecord(m->ev_d2h, m->copy_stream));
   m->d2h_pending = true;
 }
@@ -559,6 +568,7 @@ static void create(int64_t nv, int64_t ne, const double* xy, const int32_t* cell
   if (m->ab.ok) {
     m->ab_eptr.upload(m->ab.blk_eptr);
     m->ab_elems.upload(m->ab.blk_elems);
+    m->kbar_blk.alloc_zero(m->ab.blk_elems.size(), m->stream);
     m->ab_incptr.upload(m->ab.inc_ptr);
     m->ab_inc.upload(m->ab.inc_code);
     m->ab_src.upload(m->ab.src);

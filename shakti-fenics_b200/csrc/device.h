@@ -68,8 +68,9 @@ struct AssemblyPlanView {   // device arrays of prep.h AssemblyBlocks
   const uint16_t* inc_code;
   const uint32_t* src;
 };
-void launch_assemble_blocks(const AssemblyPlanView& plan, FieldPtrs f, const double* kbar, double dt, double N_bdry,
-                            const int32_t* slice_ptr, double* F, double* Jval, int want_J, DevParams p, cudaStream_t s);
+// kbar: per cell; kbar_blk: the same values in the plan's block order (kbar[blk_elems[i]]; NULL: not available)
+void launch_assemble_blocks(const AssemblyPlanView& plan, FieldPtrs f, const double* kbar, const double* kbar_blk, double dt,
+                            double N_bdry, const int32_t* slice_ptr, double* F, double* Jval, int want_J, DevParams p, cudaStream_t s);
 void launch_apply_bc(int32_t n_owned, const uint8_t* isbc, const double* N, double N_bdry,
                      const int32_t* diag_pos, double* F, double* Jval, int want_J, cudaStream_t s);
 

@@ -619,17 +619,17 @@ __device__ __forceinline__ void element_FJ_staged2(const int v[3], const double*
 template <int CAP, int VCAP>
 __global__ void __launch_bounds__(128, 4)
 assemble_blocks_v2_kernel(int32_t n_owned, int32_t rows_per_block, const int32_t* __restrict__ blk_eptr,
-                          const int32_t* __restrict__ blk_elems, const uint16_t* __restrict__ blk_lv,
+                          const uint16_t* __restrict__ blk_lv,
                           const int32_t* __restrict__ blk_hptr, const int32_t* __restrict__ blk_halo,
                           const int32_t* __restrict__ inc_ptr, const uint16_t* __restrict__ inc_code,
-                          const uint32_t* __restrict__ src, FieldPtrs f, const double* __restrict__ kbar, double dt,
+                          const uint32_t* __restrict__ src, FieldPtrs f, const double* __restrict__ kbar_blk, double dt,
                           double N_bdry, const int32_t* __restrict__ slice_ptr, double* __restrict__ F,
                           double* __restrict__ Jval, int want_J, DevParams p) {
   extern __shared__ __align__(16) double smem[];
   double* sV = smem;                               // [WFIELDS][VCAP]
   double* sK = smem + (size_t)WFIELDS * VCAP;      // [12][CAP]: F0..F2, J00..J22
-  uint8_t* sBC = reinterpret_cast<uint8_t*>(sK + (size_t)12 * CAP);   // [VCAP]
-  __shared__ __align__(8) uint64_t bar;
+  uint64_t& bar = *reinterpret_cast<uint64_t*>(sK + (size_t)12 * CAP);   // mbarrier of the bulk copies
+  uint8_t* sBC = reinterpret_cast<uint8_t*>(sK + (size_t)12 * CAP + 1);   // [VCAP]
   const int32_t r0 = blockIdx.x * rows_per_block;
   const int32_t nrows = min(rows_per_block, n_owned - r0);
   const int32_t h0 = blk_hptr[blockIdx.x], nh = blk_hptr[blockIdx.x + 1] - h0;
@@ -642,8 +642,8 @@ assemble_blocks_v2_kernel(int32_t n_owned, int32_t rows_per_block, const int32_t
 #pragma unroll
     for (int k = 0; k < WFIELDS; ++k) bulk_g2s(sV + k * VCAP, fld[k] + r0, (uint32_t)(nrows * sizeof(double)), &bar);
   }
-  // cell ids, Kbar and block-local vertex ids of this thread's cells are requested first: the chain
-  // blk_elems -> kbar would otherwise be exposed at the start of every cell
+  // Kbar (already in block order: no cell-id indirection) and the block-local vertex ids of this thread's
+  // cells are requested first, so that their latency overlaps the staging
   constexpr int kCellsPre = 4;
   const int32_t e0 = blk_eptr[blockIdx.x], e1 = blk_eptr[blockIdx.x + 1];
   double kb_pre[kCellsPre];
@@ -656,7 +656,7 @@ assemble_blocks_v2_kernel(int32_t n_owned, int32_t rows_per_block, const int32_t
       const uint16_t* lv = blk_lv + 3 * (size_t)(e0 + le);
       lv01_pre[c] = (uint32_t)lv[0] | ((uint32_t)lv[1] << 16);
       lv2_pre[c] = lv[2];
-      kb_pre[c] = kbar[blk_elems[e0 + le]];
+      kb_pre[c] = kbar_blk[e0 + le];
     }
   }
   // ---- phase 0b: halo vertices (and everything, for the last partial block) by per-thread loads
@@ -686,7 +686,7 @@ assemble_blocks_v2_kernel(int32_t n_owned, int32_t rows_per_block, const int32_t
     } else {
       const uint16_t* lv = blk_lv + 3 * (size_t)(e0 + le);
       v[0] = lv[0]; v[1] = lv[1]; v[2] = lv[2];
-      kb = kbar[blk_elems[e0 + le]];
+      kb = kbar_blk[e0 + le];
     }
     ElemOut o;
     double Nv[3];
@@ -701,7 +701,8 @@ assemble_blocks_v2_kernel(int32_t n_owned, int32_t rows_per_block, const int32_t
     }
   }
   // ---- phase 2 (first loads issued before the barrier, see the version above)
-  constexpr int kPre = 8;
+  constexpr int kPre = 8, kIncPre = 8;
+  uint16_t incpre[kIncPre];
   const bool has_row = (int32_t)threadIdx.x < nrows;
   const int32_t row = r0 + threadIdx.x;
   int32_t base = 0, w = 0, ib = 0, ie = 0;
@@ -712,6 +713,8 @@ assemble_blocks_v2_kernel(int32_t n_owned, int32_t rows_per_block, const int32_t
     w = (slice_ptr[slice + 1] - base) >> 5;
     ib = inc_ptr[row];
     ie = inc_ptr[row + 1];
+#pragma unroll
+    for (int k = 0; k < kIncPre; ++k) incpre[k] = ib + k < ie ? inc_code[ib + k] : (uint16_t)0xFFFFu;
     if (want_J) {
 #pragma unroll
       for (int k = 0; k < kPre; ++k) pre[k] = k < w ? src[base + 32 * k + (row & 31)] : 0xFFFFFFFFu;
@@ -721,7 +724,16 @@ assemble_blocks_v2_kernel(int32_t n_owned, int32_t rows_per_block, const int32_t
   if (!has_row) return;
   const bool rbc = sBC[threadIdx.x] != 0;
   double Fr = 0.0, Jd = 0.0;
-  for (int32_t k = ib; k < ie; ++k) {
+#pragma unroll
+  for (int k = 0; k < kIncPre; ++k) {
+    const uint32_t code = incpre[k];
+    if (code != 0xFFFFu) {
+      const uint32_t le = code >> 2, a = code & 3u;
+      Fr += sK[a * CAP + le];
+      Jd += sK[(3 + 4 * a) * CAP + le];
+    }
+  }
+  for (int32_t k = ib + kIncPre; k < ie; ++k) {   // vertices of valence > kIncPre
     const uint32_t code = inc_code[k];
     const uint32_t le = code >> 2, a = code & 3u;
     Fr += sK[a * CAP + le];
@@ -750,36 +762,37 @@ assemble_blocks_v2_kernel(int32_t n_owned, int32_t rows_per_block, const int32_t
 }
 
 template <int CAP, int VCAP>
-static void launch_assemble_blocks_v2(const AssemblyPlanView& pl, FieldPtrs f, const double* kbar, double dt, double N_bdry,
+static void launch_assemble_blocks_v2(const AssemblyPlanView& pl, FieldPtrs f, const double* kbar_blk, double dt, double N_bdry,
                                       const int32_t* slice_ptr, double* F, double* Jval, int want_J, DevParams p, int dev,
                                       cudaStream_t s) {
-  constexpr size_t smem = ((size_t)WFIELDS * VCAP + (size_t)12 * CAP) * sizeof(double) + VCAP;
+  constexpr size_t smem = ((size_t)WFIELDS * VCAP + (size_t)12 * CAP + 1) * sizeof(double) + VCAP;
   static bool configured[64] = {};   // the opt-in is per device
   if (!configured[dev & 63]) {
     SHAKTI_CUDA(cudaFuncSetAttribute((assemble_blocks_v2_kernel<CAP, VCAP>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SHAKTI_CUDA(cudaFuncSetAttribute((assemble_blocks_v2_kernel<CAP, VCAP>), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     configured[dev & 63] = true;
   }
   SHAKTI_LAUNCH((assemble_blocks_v2_kernel<CAP, VCAP>), pl.n_blocks, 128, smem, s, pl.n_owned, pl.rows_per_block, pl.blk_eptr,
-                pl.blk_elems, pl.blk_lv, pl.blk_hptr, pl.blk_halo, pl.inc_ptr, pl.inc_code, pl.src, f, kbar, dt, N_bdry, slice_ptr, F,
+                pl.blk_lv, pl.blk_hptr, pl.blk_halo, pl.inc_ptr, pl.inc_code, pl.src, f, kbar_blk, dt, N_bdry, slice_ptr, F,
                 Jval, want_J, p);
 }
 
-void launch_assemble_blocks(const AssemblyPlanView& pl, FieldPtrs f, const double* kbar, double dt, double N_bdry,
-                            const int32_t* slice_ptr, double* F, double* Jval, int want_J, DevParams p, cudaStream_t s) {
+void launch_assemble_blocks(const AssemblyPlanView& pl, FieldPtrs f, const double* kbar, const double* kbar_blk, double dt,
+                            double N_bdry, const int32_t* slice_ptr, double* F, double* Jval, int want_J, DevParams p, cudaStream_t s) {
   if (pl.n_blocks == 0) return;
   int dev = 0;
   SHAKTI_CUDA(cudaGetDevice(&dev));
   static const bool use_v1 = getenv("SHAKTI_ASM_V1") != nullptr;   // A/B switch: the round-1 kernel
-  if (!use_v1 && pl.rows_per_block == 128) {
-    // compile-time capacities: (352, 226) keeps 4 blocks per SM (55.7 KB each) and covers Morton-ordered
+  if (!use_v1 && kbar_blk && pl.rows_per_block == 128) {
+    // compile-time capacities: (350, 226) keeps 4 blocks per SM (55.5 KB each) and covers Morton-ordered
     // triangulations of structured-like density (C2-C5: at most 350 cells, 226 vertices per block);
     // (400, 256) is the roomier instance (3 blocks per SM); anything larger runs the runtime-stride kernel
-    if (pl.cap <= 352 && pl.vcap <= 226) {
-      launch_assemble_blocks_v2<352, 226>(pl, f, kbar, dt, N_bdry, slice_ptr, F, Jval, want_J, p, dev, s);
+    if (pl.cap <= 350 && pl.vcap <= 226) {
+      launch_assemble_blocks_v2<350, 226>(pl, f, kbar_blk, dt, N_bdry, slice_ptr, F, Jval, want_J, p, dev, s);
       return;
     }
     if (pl.cap <= 400 && pl.vcap <= 256) {
-      launch_assemble_blocks_v2<400, 256>(pl, f, kbar, dt, N_bdry, slice_ptr, F, Jval, want_J, p, dev, s);
+      launch_assemble_blocks_v2<400, 256>(pl, f, kbar_blk, dt, N_bdry, slice_ptr, F, Jval, want_J, p, dev, s);
       return;
     }
   }
@@ -1341,6 +1354,11 @@ __global__ void readback_kernel(const double* __restrict__ src, double* __restri
 }
 void launch_readback(const double* src, double* dst_host, int count, cudaStream_t s) {
   if (count <= 0) return;
+  const char* mode = getenv("SHAKTI_READBACK");   // "memcpy": copy engine (A/B switch, read per call)
+  if (mode && mode[0] == 'm' && mode[1] == 'e') {
+    SHAKTI_CUDA(cudaMemcpyAsync(dst_host, src, sizeof(double) * count, cudaMemcpyDeviceToHost, s));
+    return;
+  }
   SHAKTI_LAUNCH(readback_kernel, 1, 64, 0, s, src, dst_host, count);
 }
 
