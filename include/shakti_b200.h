@@ -235,6 +235,9 @@ int shakti_save_outputs_async(shakti_model* m, double* b_out, double* N_out, dou
 /* Page-locked host memory for those buffers (cudaMallocHost / cudaFreeHost). */
 int shakti_alloc_pinned(int64_t bytes, void** out);
 int shakti_free_pinned(void* p);
+/* Diagnostic: GB/s of cudaMemcpyAsync host->device / device->host for `host` (any host pointer) and the host
+ * milliseconds each enqueue took (enqueue_ms[0] h2d, [1] d2h): tells page-locked from pageable memory. */
+int shakti_debug_copy_bw(void* host, int64_t bytes, int reps, double* h2d_gbs, double* d2h_gbs, double* enqueue_ms);
 
 /* ---------------------------------------------------------------- micro-benchmarks
  * Launch one kernel `reps` times on the library stream and return the mean device time per

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <memory>
 
 #include "amg.h"
@@ -1132,6 +1133,44 @@ int shakti_save_outputs_async(shakti_model* m, double* b_out, double* N_out, dou
   SHAKTI_REQUIRE(m, "null model");
   use_device(m);
   shakti::save_outputs_async(m, b_out, N_out, qx_out, qy_out, owned_only);
+  SHAKTI_CATCH
+}
+
+// Diagnostic: bandwidth of cudaMemcpyAsync between `host` (any host pointer) and a scratch device buffer,
+// timed with CUDA events on a private stream, and the host time the enqueue itself takes (a pageable
+// pointer makes the "async" call block while the driver stages the data).
+int shakti_debug_copy_bw(void* host, int64_t bytes, int reps, double* h2d_gbs, double* d2h_gbs, double* enqueue_ms) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(host && bytes > 0 && reps > 0 && h2d_gbs && d2h_gbs && enqueue_ms, "bad arguments");
+  void* dev = nullptr;
+  SHAKTI_CUDA(cudaMalloc(&dev, (size_t)bytes));
+  cudaStream_t st;
+  SHAKTI_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  cudaEvent_t e0, e1;
+  SHAKTI_CUDA(cudaEventCreate(&e0));
+  SHAKTI_CUDA(cudaEventCreate(&e1));
+  for (int dir = 0; dir < 2; ++dir) {
+    SHAKTI_CUDA(cudaStreamSynchronize(st));
+    timespec t0, t1;
+    SHAKTI_CUDA(cudaEventRecord(e0, st));
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int i = 0; i < reps; ++i) {
+      if (dir == 0) SHAKTI_CUDA(cudaMemcpyAsync(dev, host, (size_t)bytes, cudaMemcpyHostToDevice, st));
+      else SHAKTI_CUDA(cudaMemcpyAsync(host, dev, (size_t)bytes, cudaMemcpyDeviceToHost, st));
+    }
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    SHAKTI_CUDA(cudaEventRecord(e1, st));
+    SHAKTI_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    SHAKTI_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double gbs = (double)bytes * reps / 1e9 / (ms / 1e3);
+    if (dir == 0) { *h2d_gbs = gbs; enqueue_ms[0] = ((t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6) / reps; }
+    else { *d2h_gbs = gbs; enqueue_ms[1] = ((t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6) / reps; }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaStreamDestroy(st);
+  cudaFree(dev);
   SHAKTI_CATCH
 }
 

@@ -782,7 +782,9 @@ void launch_assemble_blocks(const AssemblyPlanView& pl, FieldPtrs f, const doubl
   if (pl.n_blocks == 0) return;
   int dev = 0;
   SHAKTI_CUDA(cudaGetDevice(&dev));
-  static const bool use_v1 = getenv("SHAKTI_ASM_V1") != nullptr;   // A/B switch: the round-1 kernel
+  // v2 (compile-time strides, bulk-copy staging) executes 8 % fewer instructions but measured SLOWER at C4
+  // (2.31-2.53 ms vs 2.21 ms, profiles/r2_assembly.md), so it is opt-in: SHAKTI_ASM_V2=1
+  static const bool use_v1 = getenv("SHAKTI_ASM_V2") == nullptr;
   if (!use_v1 && kbar_blk && pl.rows_per_block == 128) {
     // compile-time capacities: (350, 226) keeps 4 blocks per SM (55.5 KB each) and covers Morton-ordered
     // triangulations of structured-like density (C2-C5: at most 350 cells, 226 vertices per block);
