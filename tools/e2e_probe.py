@@ -25,23 +25,23 @@ def run(label, readback, chunk, use_in, use_out):
     os.environ["SHAKTI_READBACK"] = readback
     os.environ["SHAKTI_D2H_CHUNK_MB"] = str(chunk)
     torch.cuda.synchronize()
+    st0 = m.stats()
+    first = step
     t0 = time.perf_counter()
+    nits = []
     for i in range(K):
         outs = [b.array.ctypes.data for b in sets[i % 2]] if use_out else [None] * 4
-        m.step_host_async(dts[step], h_in.array.ctypes.data if use_in else None, *outs, owned_only=True)
+        nits.append(m.step_host_async(dts[step], h_in.array.ctypes.data if use_in else None, *outs, owned_only=True)[0])
         step += 1
     m.wait_outputs()
     torch.cuda.synchronize()
     ms = 1e3 * (time.perf_counter() - t0) / K
-    print(json.dumps(dict(label=label, readback=readback, chunk_mb=chunk, h2d=use_in, d2h=use_out, ms_per_step=round(ms, 2))), flush=True)
+    st1 = m.stats()
+    print(json.dumps(dict(label=label, readback=readback, chunk_mb=chunk, h2d=use_in, d2h=use_out, ms_per_step=round(ms, 2),
+                          first_step=first, newton=nits, krylov_per_step=(st1["linear_its"] - st0["linear_its"]) / K,
+                          refreshes=st1["amg_refreshes"] - st0["amg_refreshes"])), flush=True)
 
-run("no copies", "mapped", 8, False, False)
-run("no copies", "memcpy", 8, False, False)
-run("h2d only", "mapped", 8, True, False)
-run("d2h only", "mapped", 8, False, True)
-run("d2h only", "memcpy", 8, False, True)
-run("d2h only", "mapped", 100000, False, True)
-run("d2h only", "memcpy", 100000, False, True)
-run("both", "mapped", 8, True, True)
-run("both", "memcpy", 8, True, True)
-run("both", "memcpy", 2, True, True)
+for rep in range(3):
+    run("no copies", "mapped", 8, False, False)
+    run("both", "mapped", 8, True, True)
+    run("both", "memcpy", 8, True, True)
