@@ -202,6 +202,12 @@ int shakti_update_b(shakti_model* m, double dt);
 int shakti_update_q_melt(shakti_model* m);
 /* solvers.py:228-229 */
 int shakti_copy_N_to_N_n(shakti_model* m);
+/* Device-side snapshot of the time-dependent state (N, N_n, b, q, melt_n and the solver's convergence history)
+ * and return to it: lets a caller retry a failed step with a smaller dt, or repeat the same steps (bench.py
+ * measures the device-resident and the end-to-end rate over the SAME steps this way).  Extension: the
+ * reference has nothing like it (solvers.py:168-229 only moves forward). */
+int shakti_snapshot(shakti_model* m);
+int shakti_rollback(shakti_model* m);
 /* One whole pass of solvers.py:179-229 (without file output). */
 int shakti_step(shakti_model* m, double dt, int32_t* niter, int32_t* converged);
 /* nsteps passes with the given dt list; niter_out (nsteps int32) may be NULL. */

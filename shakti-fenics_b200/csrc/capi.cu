@@ -59,6 +59,11 @@ struct shakti_model {
   cudaEvent_t ev_snap = nullptr, ev_d2h = nullptr;
   DevBuf<double> out_stage[4];
   bool d2h_pending = false;
+  // shakti_snapshot / shakti_rollback: device-side copy of the time-dependent state
+  DevBuf<double> snap[6];
+  double snap_hist_ratio = -1.0, snap_hist_dt = 0.0, snap_residual0 = 0.0;
+  int64_t snap_steps = 0;
+  bool snap_valid = false;
   double N_bdry = 0.0;
   int64_t n_bc = 0;
   bool h0_dirty = true;
@@ -1092,6 +1097,37 @@ int shakti_step_host(shakti_model* m, double dt, const double* inputs_host, doub
   if (N_out) shakti::get_field(m, SHAKTI_F_N, N_out, 0);
   if (qx_out) shakti::get_field(m, SHAKTI_F_QX, qx_out, 0);
   if (qy_out) shakti::get_field(m, SHAKTI_F_QY, qy_out, 0);
+  SHAKTI_CATCH
+}
+
+int shakti_snapshot(shakti_model* m) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(m, "null model");
+  use_device(m);
+  const size_t nl = std::max<int32_t>(m->hm.n_local, 1);
+  const double* src[6] = {m->N.p, m->N_n.p, m->b.p, m->qx.p, m->qy.p, m->melt.p};
+  for (int k = 0; k < 6; ++k) {
+    if (m->snap[k].n < nl) m->snap[k].alloc(nl);
+    SHAKTI_CUDA(cudaMemcpyAsync(m->snap[k].p, src[k], sizeof(double) * nl, cudaMemcpyDeviceToDevice, m->stream));
+  }
+  m->snap_hist_ratio = m->hist_ratio; m->snap_hist_dt = m->hist_dt; m->snap_residual0 = m->residual0;
+  m->snap_steps = m->st.steps;
+  m->snap_valid = true;
+  SHAKTI_CATCH
+}
+
+int shakti_rollback(shakti_model* m) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(m && m->snap_valid, "no snapshot to roll back to");
+  use_device(m);
+  const size_t nl = std::max<int32_t>(m->hm.n_local, 1);
+  double* dst[6] = {m->N.p, m->N_n.p, m->b.p, m->qx.p, m->qy.p, m->melt.p};
+  for (int k = 0; k < 6; ++k)
+    SHAKTI_CUDA(cudaMemcpyAsync(dst[k], m->snap[k].p, sizeof(double) * nl, cudaMemcpyDeviceToDevice, m->stream));
+  m->hist_ratio = m->snap_hist_ratio; m->hist_dt = m->snap_hist_dt; m->residual0 = m->snap_residual0;
+  // the step counter goes back too, and the AMG hierarchy (numbers of a later state) is renewed at the next solve
+  m->st.steps = m->snap_steps;
+  m->step_of_refresh = -1000000;
   SHAKTI_CATCH
 }
 

@@ -397,6 +397,12 @@ class Model:
     def copy_N_to_N_n(self):
         _check(self.lib.shakti_copy_N_to_N_n(self._h))
 
+    def snapshot(self):
+        _check(self.lib.shakti_snapshot(self._h))
+
+    def rollback(self):
+        _check(self.lib.shakti_rollback(self._h))
+
     def step(self, dt):
         it, cv = C.c_int32(0), C.c_int32(0)
         _check(self.lib.shakti_step(self._h, C.c_double(dt), C.byref(it), C.byref(cv)))

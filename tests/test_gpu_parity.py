@@ -382,3 +382,20 @@ def test_async_outputs_equal_get_field():
             assert np.array_equal(got.array, ref[own] if po else ref)
     finally:
         m1.close(); m2.close()
+
+
+def test_snapshot_and_rollback_repeat_the_same_steps():
+    c = make_case(seed=25)
+    m = make_model(*c)
+    try:
+        m.run([360.0, DT])
+        m.snapshot()
+        its_a = list(m.run([DT, DT]))
+        Na, ba = m.get_field("N"), m.get_field("b")
+        m.rollback()
+        assert m.stats()["steps"] == 2
+        its_b = list(m.run([DT, DT]))
+        assert its_a == its_b
+        assert relinf(m.get_field("N"), Na) < 1e-10 and relinf(m.get_field("b"), ba) < 1e-10
+    finally:
+        m.close()
