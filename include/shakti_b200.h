@@ -153,6 +153,22 @@ int shakti_get_field(shakti_model* m, int field, double* dst, int is_device);
 int shakti_set_flux(shakti_model* m, const double* q_interleaved, int is_device);
 int shakti_get_flux(shakti_model* m, double* q_interleaved, int is_device);
 
+/* model_setup data ingestion on the device (reference model_setup.py:68-91).
+ * shakti_interp_grid_to_field: bilinear interpolation (linear extrapolation outside the grid) of a gridded
+ *   field f_yx[iy*nx + ix] given on ascending axes xg[nx], yg[ny] onto the mesh nodes, written straight into
+ *   vertex field `field` -- RegularGridInterpolator((x, y), f.T, bounds_error=False, fill_value=None) of
+ *   model_setup.interp_data, without the host round trip of the nodal array.
+ * shakti_polygon_to_field: 1.0 at nodes inside the closed polygon poly_xy[n_poly][2] (even-odd rule), else 0.0
+ *   -- the lake indicator of model_setup.set_lake_bdry.
+ * The two functions without a model do the same for arbitrary host points (parity hooks). */
+int shakti_interp_grid_to_field(shakti_model* m, int field, int32_t nx, int32_t ny, const double* xg, const double* yg,
+                                const double* f_yx);
+int shakti_polygon_to_field(shakti_model* m, int field, int32_t n_poly, const double* poly_xy);
+int shakti_interp_grid(int64_t n, const double* px, const double* py, int32_t nx, int32_t ny, const double* xg,
+                       const double* yg, const double* f_yx, double* out);
+int shakti_points_in_polygon(int64_t n, const double* px, const double* py, int32_t n_poly, const double* poly_xy,
+                             double* out);
+
 /* Dirichlet dofs and value: solvers.py:17-26 (get_bcs).  n_dofs == 0 <=> outflow_on False. */
 int shakti_set_dirichlet(shakti_model* m, const int32_t* dofs, int64_t n_dofs, double value);
 /* Boundary facets whose vertices all satisfy marker[v] != 0 -> dofs; replaces

@@ -1131,6 +1131,77 @@ int shakti_rollback(shakti_model* m) {
   SHAKTI_CATCH
 }
 
+// ---- model_setup data ingestion on the device: the grid / polygon comes from the host, the
+// mesh nodes are the model's own (already resident), the result lands directly in a vertex field
+int shakti_interp_grid_to_field(shakti_model* m, int field, int32_t nx, int32_t ny, const double* xg, const double* yg,
+                                const double* f_yx) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(m && xg && yg && f_yx && nx >= 2 && ny >= 2, "bad grid arguments");
+  SHAKTI_REQUIRE(field >= 0 && field < SHAKTI_F_COUNT && field != SHAKTI_F_RESIDUAL, "field is not writable");
+  use_device(m);
+  DevBuf<double> dx, dy, df;
+  dx.upload(xg, (size_t)nx);
+  dy.upload(yg, (size_t)ny);
+  df.upload(f_yx, (size_t)nx * ny);
+  launch_interp_grid(m->hm.n_local, m->x.p, m->y.p, nx, ny, dx.p, dy.p, df.p, field_ptr(m, field), m->stream);
+  if (field == SHAKTI_F_Z_B || field == SHAKTI_F_Z_S) m->h0_dirty = true;
+  if (field != SHAKTI_F_INPUTS) m->hist_ratio = -1.0;
+  SHAKTI_CUDA(cudaStreamSynchronize(m->stream));
+  SHAKTI_CATCH
+}
+
+int shakti_polygon_to_field(shakti_model* m, int field, int32_t n_poly, const double* poly_xy) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(m && poly_xy && n_poly >= 3, "a polygon needs at least 3 vertices");
+  SHAKTI_REQUIRE(field >= 0 && field < SHAKTI_F_COUNT && field != SHAKTI_F_RESIDUAL, "field is not writable");
+  use_device(m);
+  DevBuf<double> dp;
+  dp.upload(poly_xy, (size_t)2 * n_poly);
+  launch_points_in_polygon(m->hm.n_local, m->x.p, m->y.p, n_poly, dp.p, field_ptr(m, field), m->stream);
+  if (field != SHAKTI_F_INPUTS) m->hist_ratio = -1.0;
+  SHAKTI_CUDA(cudaStreamSynchronize(m->stream));
+  SHAKTI_CATCH
+}
+
+// the same two operations for arbitrary points, without a model (host arrays in and out)
+int shakti_interp_grid(int64_t n, const double* px, const double* py, int32_t nx, int32_t ny, const double* xg,
+                       const double* yg, const double* f_yx, double* out) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(n >= 0 && px && py && xg && yg && f_yx && out && nx >= 2 && ny >= 2, "bad arguments");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    throw Error(SHAKTI_ERR_NO_DEVICE, "no CUDA device: the SHAKTI B200 path has no CPU fallback");
+  }
+  DevBuf<double> dpx, dpy, dx, dy, df, dout;
+  dpx.upload(px, (size_t)n); dpy.upload(py, (size_t)n);
+  dx.upload(xg, (size_t)nx); dy.upload(yg, (size_t)ny); df.upload(f_yx, (size_t)nx * ny);
+  dout.alloc((size_t)std::max<int64_t>(n, 1));
+  launch_interp_grid(n, dpx.p, dpy.p, nx, ny, dx.p, dy.p, df.p, dout.p, 0);
+  SHAKTI_CUDA(cudaStreamSynchronize(0));
+  if (n) SHAKTI_CUDA(cudaMemcpy(out, dout.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  SHAKTI_CATCH
+}
+
+int shakti_points_in_polygon(int64_t n, const double* px, const double* py, int32_t n_poly, const double* poly_xy,
+                             double* out) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(n >= 0 && px && py && poly_xy && out && n_poly >= 3, "bad arguments");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    throw Error(SHAKTI_ERR_NO_DEVICE, "no CUDA device: the SHAKTI B200 path has no CPU fallback");
+  }
+  DevBuf<double> dpx, dpy, dp, dout;
+  dpx.upload(px, (size_t)n); dpy.upload(py, (size_t)n);
+  dp.upload(poly_xy, (size_t)2 * n_poly);
+  dout.alloc((size_t)std::max<int64_t>(n, 1));
+  launch_points_in_polygon(n, dpx.p, dpy.p, n_poly, dp.p, dout.p, 0);
+  SHAKTI_CUDA(cudaStreamSynchronize(0));
+  if (n) SHAKTI_CUDA(cudaMemcpy(out, dout.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  SHAKTI_CATCH
+}
+
 int shakti_wait_outputs(shakti_model* m) {
   SHAKTI_TRY
   SHAKTI_REQUIRE(m, "null model");

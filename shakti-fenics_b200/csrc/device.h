@@ -135,6 +135,11 @@ void launch_pointwise_mul(int64_t n, const double* a, const double* b, double sc
 void launch_fill(int64_t n, double v, double* x, cudaStream_t s);
 void launch_gather(int64_t n, const int32_t* idx, const double* src, double* dst, cudaStream_t s);   // dst[i] = src[idx[i]]
 void launch_scatter(int64_t n, const int32_t* idx, const double* src, double* dst, cudaStream_t s);  // dst[idx[i]] = src[i]
+// model_setup data ingestion on the device (reference model_setup.py:68-91)
+void launch_interp_grid(int64_t n, const double* px, const double* py, int nx, int ny, const double* xg, const double* yg,
+                        const double* f, double* out, cudaStream_t s);
+void launch_points_in_polygon(int64_t n, const double* px, const double* py, int m, const double* poly_xy, double* out,
+                              cudaStream_t s);
 void launch_head0(int64_t n, const double* z_b, const double* z_s, double ratio, double* h0, cudaStream_t s);
 void launch_interleave(int64_t n, const double* a, const double* b, double* ab, cudaStream_t s);
 void launch_deinterleave(int64_t n, const double* ab, double* a, double* b, cudaStream_t s);

@@ -1364,6 +1364,73 @@ void launch_readback(const double* src, double* dst_host, int count, cudaStream_
   SHAKTI_LAUNCH(readback_kernel, 1, 64, 0, s, src, dst_host, count);
 }
 
+// ------------------------------------------------------------------ model_setup data ingestion
+// Bilinear interpolation of a gridded field f[iy][ix] (row-major, grid axes xg / yg ascending, not
+// necessarily uniform) at scattered points, linear EXTRAPOLATION outside the grid: the semantics of
+// scipy RegularGridInterpolator((x, y), f.T, bounds_error=False, fill_value=None), which the reference
+// uses to bring BedMachine / ATL14 rasters onto the mesh nodes (model_setup.py:74-91).
+__device__ __forceinline__ int grid_interval(const double* __restrict__ g, int n, double v) {
+  int lo = 0, hi = n;              // first index with g[idx] > v  (searchsorted right) ...
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (g[mid] <= v) lo = mid + 1; else hi = mid;
+  }
+  return min(max(lo - 1, 0), n - 2);   // ... minus one, clipped so that [i, i+1] is a valid cell
+}
+__global__ void __launch_bounds__(256)
+interp_grid_kernel(int64_t n, const double* __restrict__ px, const double* __restrict__ py, int nx, int ny,
+                   const double* __restrict__ xg, const double* __restrict__ yg, const double* __restrict__ f,
+                   double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x = px[i], y = py[i];
+  const int ix = grid_interval(xg, nx, x), iy = grid_interval(yg, ny, y);
+  const double tx = (x - xg[ix]) / (xg[ix + 1] - xg[ix]);
+  const double ty = (y - yg[iy]) / (yg[iy + 1] - yg[iy]);
+  const double f00 = f[(size_t)iy * nx + ix], f10 = f[(size_t)iy * nx + ix + 1];
+  const double f01 = f[(size_t)(iy + 1) * nx + ix], f11 = f[(size_t)(iy + 1) * nx + ix + 1];
+  out[i] = (1.0 - tx) * (1.0 - ty) * f00 + tx * (1.0 - ty) * f10 + (1.0 - tx) * ty * f01 + tx * ty * f11;
+}
+void launch_interp_grid(int64_t n, const double* px, const double* py, int nx, int ny, const double* xg, const double* yg,
+                        const double* f, double* out, cudaStream_t s) {
+  if (n == 0) return;
+  SHAKTI_LAUNCH(interp_grid_kernel, div_up(n, 256), 256, 0, s, n, px, py, nx, ny, xg, yg, f, out);
+}
+
+// Lake indicator: even-odd rule against a closed polygon (vertices in shared memory, 1024 per pass); what
+// set_lake_bdry does point by point with shapely in the reference (model_setup.py:68-72).
+__global__ void __launch_bounds__(256)
+points_in_polygon_kernel(int64_t n, const double* __restrict__ px, const double* __restrict__ py, int m,
+                         const double* __restrict__ poly, double* __restrict__ out) {
+  __shared__ double sx[1025], sy[1025];
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const double x = i < n ? px[i] : 0.0, y = i < n ? py[i] : 0.0;
+  bool inside = false;
+  for (int base = 0; base < m; base += 1024) {
+    const int cnt = min(1024, m - base);
+    __syncthreads();
+    for (int k = threadIdx.x; k <= cnt; k += blockDim.x) {   // one extra vertex: the edge's end point
+      const int v = (base + k) % m;
+      sx[k] = poly[2 * v];
+      sy[k] = poly[2 * v + 1];
+    }
+    __syncthreads();
+    for (int k = 0; k < cnt; ++k) {
+      const double x0 = sx[k], y0 = sy[k], x1 = sx[k + 1], y1 = sy[k + 1];
+      if ((y0 > y) != (y1 > y)) {
+        const double xc = x0 + (y - y0) * (x1 - x0) / (y1 - y0);
+        if (x < xc) inside = !inside;
+      }
+    }
+  }
+  if (i < n) out[i] = inside ? 1.0 : 0.0;
+}
+void launch_points_in_polygon(int64_t n, const double* px, const double* py, int m, const double* poly, double* out,
+                              cudaStream_t s) {
+  if (n == 0) return;
+  SHAKTI_LAUNCH(points_in_polygon_kernel, div_up(n, 256), 256, 0, s, n, px, py, m, poly, out);
+}
+
 // ------------------------------------------------------------------ streaming vector kernels
 __global__ void axpy_kernel(int64_t n, double alpha, const double* __restrict__ x, double* __restrict__ y) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;

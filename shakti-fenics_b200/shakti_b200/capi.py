@@ -205,6 +205,24 @@ class HostMesh:
             self._h = None
 
 
+def interp_grid(px, py, xg, yg, f_yx):
+    """Bilinear interpolation / linear extrapolation of f_yx[iy, ix] at points (px, py) on the GPU."""
+    px, py, xg, yg, f = _f64(px), _f64(py), _f64(xg), _f64(yg), _f64(f_yx)
+    assert f.shape == (yg.size, xg.size)
+    out = np.empty(px.size)
+    _check(load().shakti_interp_grid(C.c_int64(px.size), _p(px), _p(py), C.c_int32(xg.size), C.c_int32(yg.size), _p(xg), _p(yg),
+                                     _p(f), _p(out)))
+    return out
+
+
+def points_in_polygon(px, py, poly):
+    """1.0 / 0.0 per point: inside the closed polygon poly (m, 2) by the even-odd rule, on the GPU."""
+    px, py, poly = _f64(px), _f64(py), _f64(poly)
+    out = np.empty(px.size)
+    _check(load().shakti_points_in_polygon(C.c_int64(px.size), _p(px), _p(py), C.c_int32(poly.shape[0]), _p(poly), _p(out)))
+    return out
+
+
 class PinnedArray:
     """A float64 numpy array over page-locked host memory (cudaMallocHost), freed with the object."""
 
@@ -318,6 +336,16 @@ class Model:
         n = C.c_int64(0)
         _check(self.lib.shakti_locate_dirichlet(self._h, _p(marker), _p(out), C.c_int64(self.n_vert), C.byref(n)))
         return out[: n.value].copy()
+
+    def interp_grid_to_field(self, name, xg, yg, f_yx):
+        xg, yg, f = _f64(xg), _f64(yg), _f64(f_yx)
+        assert f.shape == (yg.size, xg.size)
+        _check(self.lib.shakti_interp_grid_to_field(self._h, C.c_int(FIELDS[name]), C.c_int32(xg.size), C.c_int32(yg.size),
+                                                    _p(xg), _p(yg), _p(f)))
+
+    def polygon_to_field(self, name, poly):
+        poly = _f64(poly)
+        _check(self.lib.shakti_polygon_to_field(self._h, C.c_int(FIELDS[name]), C.c_int32(poly.shape[0]), _p(poly)))
 
     def set_quadrature(self, pts, wts):
         pts, wts = _f64(pts), _f64(wts)

@@ -20,7 +20,17 @@ _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if _PKG not in sys.path:
     sys.path.insert(0, _PKG)
 
+from shakti_b200 import capi  # noqa: E402
 from shakti_b200.fem import Function, functionspace, element  # noqa: E402
+
+
+def _gpu_available():
+    """Setup modules may be prepared on a machine without a GPU (the solve itself cannot run there)."""
+    try:
+        return capi.device_count() > 0
+    except Exception:
+        return False
+
 from solvers import solve  # noqa: E402
 
 # scalar P1 input fields: attribute name -> meaning [unit]
@@ -102,7 +112,10 @@ class model_setup:
             for j in range(self.lake_bdry.x.array.size):
                 self.lake_bdry.x.array[j] = outline.geometry.contains(Point(xyz[j, 0], xyz[j, 1])).iloc[0]
         else:                                       # plain polygon vertices
-            self.lake_bdry.x.array[:] = points_in_polygon(self.x, self.y, outline)
+            if _gpu_available():                    # even-odd test on the device (csrc: points_in_polygon_kernel)
+                self.lake_bdry.x.array[:] = capi.points_in_polygon(self.x, self.y, outline)
+            else:
+                self.lake_bdry.x.array[:] = points_in_polygon(self.x, self.y, outline)
         self.lake_bdry.x.scatter_forward()
 
     def interp_data(self, var_name, x_d, y_d, f):
@@ -111,9 +124,13 @@ class model_setup:
         xmin, xmax, ymin, ymax = self.bounds
         keep_x = (x_d >= xmin) & (x_d <= xmax)
         keep_y = (y_d >= ymin) & (y_d <= ymax)
-        interpolant = RegularGridInterpolator((x_d[keep_x], y_d[keep_y]), f[np.ix_(keep_y, keep_x)].T,
-                                              bounds_error=False, fill_value=None)
-        set_array_slice(self, f"{var_name}.x.array", interpolant(np.column_stack((self.x, self.y))))
+        x_sub, y_sub, f_sub = x_d[keep_x], y_d[keep_y], f[np.ix_(keep_y, keep_x)]
+        interpolant = RegularGridInterpolator((x_sub, y_sub), f_sub.T, bounds_error=False, fill_value=None)
+        if _gpu_available():                        # same bilinear / extrapolating rule on the device (interp_grid_kernel)
+            values = capi.interp_grid(self.x, self.y, x_sub, y_sub, f_sub)
+        else:
+            values = interpolant(np.column_stack((self.x, self.y)))
+        set_array_slice(self, f"{var_name}.x.array", values)
         get_nested_attr(self, f"{var_name}.x").scatter_forward()
         return interpolant
 

@@ -399,3 +399,36 @@ def test_snapshot_and_rollback_repeat_the_same_steps():
         assert relinf(m.get_field("N"), Na) < 1e-10 and relinf(m.get_field("b"), ba) < 1e-10
     finally:
         m.close()
+
+
+def test_device_data_ingestion_matches_scipy_and_numpy():
+    """Row f3: model_setup.interp_data / set_lake_bdry on the device -- bilinear interpolation with linear
+    extrapolation against scipy's RegularGridInterpolator (the reference's call, model_setup.py:83), the lake
+    mask against the numpy even-odd test; both also straight into a vertex field of a model."""
+    import sys
+    from pathlib import Path
+    from scipy.interpolate import RegularGridInterpolator
+    from shakti_b200 import capi
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "shakti-fenics_b200" / "source"))
+    from model_setup import points_in_polygon
+    rng = np.random.default_rng(31)
+    xg = np.sort(rng.uniform(-1e3, 101e3, 57)); yg = np.sort(rng.uniform(-2e3, 52e3, 43))
+    f = rng.standard_normal((yg.size, xg.size))
+    px = rng.uniform(-10e3, 110e3, 20000); py = rng.uniform(-10e3, 60e3, 20000)     # a good part lies outside the grid
+    ref = RegularGridInterpolator((xg, yg), f.T, bounds_error=False, fill_value=None)(np.column_stack((px, py)))
+    got = capi.interp_grid(px, py, xg, yg, f)
+    assert np.max(np.abs(got - ref)) <= 1e-12 * np.max(np.abs(ref))
+    t = np.linspace(0, 2 * np.pi, 1500, endpoint=False)                              # > 1024 vertices: two passes
+    poly = np.column_stack((50e3 + 30e3 * np.cos(t) * (1 + 0.3 * np.sin(7 * t)), 25e3 + 15e3 * np.sin(t) * (1 + 0.2 * np.cos(5 * t))))
+    assert np.array_equal(capi.points_in_polygon(px, py, poly) != 0, points_in_polygon(px, py, poly))
+    c = make_case(seed=32)
+    m = make_model(*c)
+    try:
+        xy = c[0]
+        m.interp_grid_to_field("z_b", xg, yg, f)
+        zb = RegularGridInterpolator((xg, yg), f.T, bounds_error=False, fill_value=None)(xy)
+        assert np.max(np.abs(m.get_field("z_b") - zb)) <= 1e-12 * np.max(np.abs(zb))
+        m.polygon_to_field("storage", poly)
+        assert np.array_equal(m.get_field("storage") != 0, points_in_polygon(xy[:, 0], xy[:, 1], poly))
+    finally:
+        m.close()
