@@ -56,6 +56,28 @@ def radon7():
     return bary[:, 1:3].copy(), 0.5 * np.array(wts)
 
 
+def check_degree(pts, wts, degree=7, tol=1e-14):
+    """Validate a user-supplied table (e.g. the one a FEniCSx golden dump records from Basix): weights sum to
+    the area 1/2, all points inside the reference triangle, every monomial x^a y^b with a + b <= degree
+    integrated exactly (exact value a! b! / (a + b + 2)!).  Returns the largest absolute moment error;
+    raises ValueError when the table is not a rule of that degree."""
+    from math import factorial
+    pts, wts = np.asarray(pts, dtype=np.float64), np.asarray(wts, dtype=np.float64)
+    if pts.ndim != 2 or pts.shape[1] != 2 or wts.shape != (pts.shape[0],):
+        raise ValueError("quadrature table must be pts (n,2), wts (n,)")
+    if np.any(pts < -1e-14) or np.any(pts.sum(axis=1) > 1 + 1e-14):
+        raise ValueError("quadrature point outside the reference triangle")
+    worst = 0.0
+    for a in range(degree + 1):
+        for b in range(degree + 1 - a):
+            exact = factorial(a) * factorial(b) / factorial(a + b + 2)
+            err = abs(float((wts * pts[:, 0] ** a * pts[:, 1] ** b).sum()) - exact)
+            worst = max(worst, err)
+            if err > tol + 1e-13 * exact:
+                raise ValueError(f"table does not integrate x^{a} y^{b} exactly (error {err:.2e}): not of degree {degree}")
+    return worst
+
+
 def default_table():
     """Degree-7 table used when the caller supplies none (stand-in for Basix XG-7)."""
     return gauss_jacobi_triangle(7)

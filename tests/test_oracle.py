@@ -25,6 +25,20 @@ def test_quadrature_exact_for_monomials(rule, deg):
             assert abs((w * p[:, 0] ** a * p[:, 1] ** b).sum() - exact) < 2e-16 + 1e-14 * exact
 
 
+def test_check_degree_accepts_rules_of_the_degree_and_rejects_others():
+    """Any table handed to shakti_set_quadrature / ShaktiOracle(quad=) -- in particular the one a FEniCSx golden
+    dump records from Basix -- can be validated before use."""
+    assert quadrature.check_degree(*quadrature.gauss_jacobi_triangle(7), degree=7) < 1e-15
+    assert quadrature.check_degree(*quadrature.radon7(), degree=5) < 1e-15
+    with pytest.raises(ValueError):
+        quadrature.check_degree(*quadrature.radon7(), degree=7)            # a degree-5 rule is not a degree-7 rule
+    p, w = quadrature.gauss_jacobi_triangle(7)
+    with pytest.raises(ValueError):
+        quadrature.check_degree(p, 1.001 * w, degree=7)                    # wrong area
+    with pytest.raises(ValueError):
+        quadrature.check_degree(p + np.array([0.9, 0.0]), w, degree=7)     # points outside the triangle
+
+
 def _single_element_oracle(case):
     xy = np.array(case["xy"])
     o = ShaktiOracle(xy, np.array([[0, 1, 2]], dtype=np.int32))
