@@ -448,7 +448,8 @@ def main():
                    "linear_forcing": float(m.options.linear_forcing),
                    "amg_levels": st1["amg_levels"], "amg_refreshes_in_timed_region": st1["amg_refreshes"] - st0["amg_refreshes"],
                    "amg_operator_complexity": st1["amg_operator_complexity"],
-                   "setup_seconds": setup_s, "warmup_newton_its": [int(v) for v in its_w],
+                   "setup_seconds": setup_s, "host_max_rss_gb": __import__("resource").getrusage(0).ru_maxrss / 1048576.0,
+                   "warmup_newton_its": [int(v) for v in its_w],
                    "timed_newton_its": [int(v) for v in its]},
         "roofline": roofline, "kernels": kern, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": clocks,
