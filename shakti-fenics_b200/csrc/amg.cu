@@ -392,6 +392,7 @@ amg_dense_invert_kernel(int32_t n, double* __restrict__ D, int* __restrict__ inf
 template <class TB, class TX>
 __global__ void amg_dense_apply_kernel(int32_t n, const double* __restrict__ D, const TB* __restrict__ b,
                                        TX* __restrict__ x) {
+  pdl_sync();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= n) return;
   const double* row = D + (size_t)warp * 2 * n + n;
@@ -409,6 +410,7 @@ template <class T, int KG>
 __global__ void __launch_bounds__(256)
 amg_cheby_kernel(SellViewT<T> A, const T* __restrict__ dinv, const T* __restrict__ b, const T* __restrict__ x,
                  T* __restrict__ d, T* __restrict__ x_out, T c1, T c2) {
+  pdl_sync();
   int32_t row;
   T acc = 0;
   if (KG == 1) {
@@ -448,15 +450,16 @@ template <class T>
 static void launch_cheby(SellViewT<T> A, const T* dinv, const T* b, const T* x, T* d, T* x_out, double c1, double c2, cudaStream_t s) {
   // (a variant interleaving two slices per warp was measured slower: 193 vs 179 ms per step)
   if (A.n_rows < kChebyWideRowsBelow)
-    SHAKTI_LAUNCH((amg_cheby_kernel<T, 8>), A.n_slices, 256, 0, s, A, dinv, b, x, d, x_out, (T)c1, (T)c2);
+    SHAKTI_LAUNCH_PDL((amg_cheby_kernel<T, 8>), A.n_slices, 256, 0, s, A, dinv, b, x, d, x_out, (T)c1, (T)c2);
   else
-    SHAKTI_LAUNCH((amg_cheby_kernel<T, 1>), div_up((int64_t)A.n_slices * 32, 256), 256, 0, s, A, dinv, b, x, d, x_out, (T)c1, (T)c2);
+    SHAKTI_LAUNCH_PDL((amg_cheby_kernel<T, 1>), div_up((int64_t)A.n_slices * 32, 256), 256, 0, s, A, dinv, b, x, d, x_out, (T)c1, (T)c2);
 }
 
 // first Chebyshev step from a zero guess: d = (dinv b)/theta ; x = d
 template <class T>
 __global__ void amg_cheby_first_kernel(int32_t n, const T* __restrict__ dinv, const T* __restrict__ b, T inv_theta,
                                        T* __restrict__ d, T* __restrict__ x) {
+  pdl_sync();
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const T v = dinv[i] * b[i] * inv_theta;
@@ -533,6 +536,7 @@ __global__ void amg_compact_kernel(int32_t N, int32_t nmax, int32_t nranks, cons
 // out[i] = src[map[i]]
 template <class T>
 __global__ void amg_gather_map_kernel(int32_t n, const int32_t* __restrict__ map, const T* __restrict__ src, T* __restrict__ out) {
+  pdl_sync();
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = src[map[i]];
 }
@@ -1272,7 +1276,7 @@ static void smooth(Amg::Impl& I, AmgLevel& L, const DevSell& A, const T* b, int 
     double rho = 1.0 / sigma;
     int k0 = 0;
     if (zero_guess) {
-      if (L.n) SHAKTI_LAUNCH((amg_cheby_first_kernel<T>), div_up(L.n, 256), 256, 0, s, L.n, v.dinv.p, b, (T)(1.0 / theta), v.d.p, v.x.p);
+      if (L.n) SHAKTI_LAUNCH_PDL((amg_cheby_first_kernel<T>), div_up(L.n, 256), 256, 0, s, L.n, v.dinv.p, b, (T)(1.0 / theta), v.d.p, v.x.p);
       k0 = 1;
     }
     for (int k = k0; k < sweeps; ++k) {
@@ -1325,7 +1329,7 @@ static void vcycle(Amg::Impl& I, const DevSell& Afine) {
         CommSerialScope serial;
         tx = I.tail->cycle<T>(I.tailM);
       }
-      if (L.n_cols) SHAKTI_LAUNCH((amg_gather_map_kernel<T>), div_up(L.n_cols, 256), 256, 0, s, L.n_cols, I.tail_gid.p, tx, v.x.p);
+      if (L.n_cols) SHAKTI_LAUNCH_PDL((amg_gather_map_kernel<T>), div_up(L.n_cols, 256), 256, 0, s, L.n_cols, I.tail_gid.p, tx, v.x.p);
       break;
     }
     if (L.last) {
@@ -1339,7 +1343,7 @@ static void vcycle(Amg::Impl& I, const DevSell& Afine) {
           SHAKTI_LAUNCH((amg_dense_apply_kernel<double, double>), div_up((int64_t)N * 32, 128), 128, 0, s, N, I.dense.p, I.cglob.p, I.csol.p);
           if (L.n) SHAKTI_LAUNCH((amg_convert_kernel<double, T>), div_up(L.n, 256), 256, 0, s, L.n, I.csol.p + I.coff_me, v.x.p);
         } else if (L.n) {
-          SHAKTI_LAUNCH((amg_dense_apply_kernel<T, T>), div_up((int64_t)L.n * 32, 128), 128, 0, s, L.n, I.dense.p, v.b.p, v.x.p);
+          SHAKTI_LAUNCH_PDL((amg_dense_apply_kernel<T, T>), div_up((int64_t)L.n * 32, 128), 128, 0, s, L.n, I.dense.p, v.b.p, v.x.p);
         }
       } else {
         smooth<T>(I, L, A, v.b.p, 8, true, false);

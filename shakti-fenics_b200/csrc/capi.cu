@@ -752,7 +752,7 @@ int shakti_default_options(shakti_options* o) {
   o->newton_rtol = 1e-9; o->newton_atol = 1e-10; o->newton_max_it = 50; o->newton_r0 = SHAKTI_R0_INITIAL_RESIDUAL;
   o->linear_solver = SHAKTI_KSP_GMRES; o->precond = SHAKTI_PC_AMG;
   o->linear_rtol = 1e-12; o->linear_atol = 0.0; o->linear_max_it = 2000; o->gmres_restart = 40;
-  o->amg_refresh_every = 2; o->amg_max_levels = 12; o->amg_coarse_size = 128; o->amg_presmooth = 2; o->amg_postsmooth = 2;
+  o->amg_refresh_every = 2; o->amg_max_levels = 12; o->amg_coarse_size = 256; o->amg_presmooth = 2; o->amg_postsmooth = 2;
   o->amg_smoother_omega = 0.67; o->amg_prolong_omega = 0.67; o->amg_strength_theta = 0.08; o->amg_cheby_ratio = 5.0;
   o->amg_smoother = 1; o->amg_fp32_cycle = 1; o->amg_cuda_graph = 1; o->amg_smoother_halo = 1;
   o->b_min = 1.0e-5; o->assembly_kernel = 0; o->reorder = 1;

@@ -250,6 +250,7 @@ p2p_gather_kernel(int nranks, int me, int stride, char* const* __restrict__ peer
                   const unsigned long long* __restrict__ my_flag, const double* __restrict__ my_buf, unsigned long long* ctr,
                   const TS* local, int count, const int32_t* __restrict__ off, const int32_t* __restrict__ cnt,
                   TO* out, int* err) {   // local may alias out (in-place all-reduce): no __restrict__
+  pdl_sync();
   const unsigned long long e = *(volatile unsigned long long*)ctr + 1;
   const size_t slot = (size_t)(e & 1) * nranks * stride;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
@@ -346,7 +347,7 @@ void P2pGather::allgatherv(const TS* local, TO* out, cudaStream_t s) {
   const unsigned long long* mf = reinterpret_cast<const unsigned long long*>(p2p_local(flag_off));
   const double* mb = reinterpret_cast<const double*>(p2p_local(buf_off));
   const int blocks = std::max(1, std::min(8, (max_count + 1023) / 1024));
-  SHAKTI_LAUNCH((p2p_gather_kernel<0, TS, TO>), blocks, 256, 0, s, nr, me, stride, peer_buf.p, peer_flag.p, mf, mb, ctr.p, local, my_count,
+  SHAKTI_LAUNCH_PDL((p2p_gather_kernel<0, TS, TO>), blocks, 256, 0, s, nr, me, stride, peer_buf.p, peer_flag.p, mf, mb, ctr.p, local, my_count,
                 off.p, cnt.p, out, g_p2p.err_dev);
 }
 template void P2pGather::allgatherv<float, float>(const float*, float*, cudaStream_t);
@@ -502,6 +503,7 @@ __global__ void __launch_bounds__(256)
 halo_p2p_kernel(int npeers, const HaloPeerDev* __restrict__ peers, char* my_stage, unsigned long long slot_stride,
                 const unsigned long long* __restrict__ my_flags, unsigned long long* ctr, const T* __restrict__ src,
                 const int32_t* __restrict__ idx, T* dst, int width, int* err) {
+  pdl_sync();
   const unsigned long long e = *(volatile unsigned long long*)ctr + 1;
   const unsigned long long par = e & 1ull;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
@@ -591,7 +593,7 @@ void HaloPlan::exchange_p2p(const T* src, const int32_t* idx, T* dst, int width,
   if (peers.empty()) return;
   const int64_t work = (int64_t)std::max(n_send, n_recv) * width;
   const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(16, (work + 2047) / 2048));
-  SHAKTI_LAUNCH((halo_p2p_kernel<T>), blocks, 256, 0, s, (int)peers.size(), dpeers.p, p2p_local(stage_off), slot_stride,
+  SHAKTI_LAUNCH_PDL((halo_p2p_kernel<T>), blocks, 256, 0, s, (int)peers.size(), dpeers.p, p2p_local(stage_off), slot_stride,
                 reinterpret_cast<const unsigned long long*>(p2p_local(flag_off)), ctr.p, src, idx, dst, width, g_p2p.err_dev);
 }
 template void HaloPlan::exchange_p2p<double>(const double*, const int32_t*, double*, int, cudaStream_t);

@@ -46,6 +46,39 @@ extern int64_t g_kernel_launches;
                                                  cudaGetErrorString(e_)); \
   } while (0)
 
+// Programmatic dependent launch (SHAKTI_PDL=1, experimental): the kernels of the V-cycle are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so the NEXT kernel of the chain is scheduled while the
+// current one drains and blocks in `griddepcontrol.wait` until its predecessor has completed and flushed.
+// Every kernel launched this way calls pdl_sync() before it touches memory; launched normally that is a no-op.
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <class K, class... Args>
+inline cudaError_t launch_maybe_pdl(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+#define SHAKTI_LAUNCH_PDL(kernel, grid, block, smem, stream, ...)                                \
+  do {                                                                                           \
+    cudaError_t e_ = ::shakti::launch_maybe_pdl(kernel, dim3(grid), dim3(block), (smem), (stream), __VA_ARGS__); \
+    ++::shakti::g_kernel_launches;                                                               \
+    if (e_ != cudaSuccess)                                                                       \
+      throw ::shakti::Error(SHAKTI_ERR_CUDA, std::string(#kernel) + " launch: " + cudaGetErrorString(e_)); \
+  } while (0)
+#endif
+
 template <class T>
 struct DevBuf {
   T* p = nullptr;

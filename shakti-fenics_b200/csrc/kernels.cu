@@ -12,6 +12,11 @@ namespace shakti {
 
 int64_t g_kernel_launches = 0;
 
+bool pdl_enabled() {
+  static const bool on = getenv("SHAKTI_PDL") != nullptr && atoi(getenv("SHAKTI_PDL")) != 0;
+  return on;
+}
+
 // ---- diagnostic phase timer (common.h)
 static std::vector<std::pair<std::string, std::pair<double, int64_t>>> g_phases;
 bool phase_trace_enabled() {
@@ -1046,6 +1051,7 @@ template <int MODE, class T, int KG>
 __global__ void __launch_bounds__(256)
 spmv_sell_kernel(SellViewT<T> A, const T* __restrict__ x, const T* __restrict__ b, const T* __restrict__ dinv, T omega,
                  T* __restrict__ y) {
+  pdl_sync();
   int32_t row;
   T acc;
   if (!sell_row_dot<T, KG>(A, x, row, acc)) return;
@@ -1059,11 +1065,11 @@ template <int MODE, class T>
 static void spmv_launch(SellViewT<T> A, const T* x, const T* b, const T* dinv, double omega, T* y, cudaStream_t s) {
   if (A.n_rows == 0) return;
   if (A.n_rows < kWideRowsBelow) {
-    SHAKTI_LAUNCH((spmv_sell_kernel<MODE, T, 8>), A.n_slices, 256, 0, s, A, x, b, dinv, (T)omega, y);
+    SHAKTI_LAUNCH_PDL((spmv_sell_kernel<MODE, T, 8>), A.n_slices, 256, 0, s, A, x, b, dinv, (T)omega, y);
     return;
   }
   const int64_t threads = (int64_t)A.n_slices * 32;
-  SHAKTI_LAUNCH((spmv_sell_kernel<MODE, T, 1>), div_up(threads, 256), 256, 0, s, A, x, b, dinv, (T)omega, y);
+  SHAKTI_LAUNCH_PDL((spmv_sell_kernel<MODE, T, 1>), div_up(threads, 256), 256, 0, s, A, x, b, dinv, (T)omega, y);
 }
 template <class T> void launch_spmv(SellViewT<T> A, const T* x, T* y, cudaStream_t s) { spmv_launch<SPMV_SET, T>(A, x, nullptr, nullptr, 0, y, s); }
 template <class T> void launch_spmv_add(SellViewT<T> A, const T* x, T* y, cudaStream_t s) { spmv_launch<SPMV_ADD, T>(A, x, nullptr, nullptr, 0, y, s); }
@@ -1102,6 +1108,7 @@ void DevSell::refresh_f32(cudaStream_t s) const {
 }
 template <class T>
 __global__ void scaled_mul_kernel(int64_t n, const T* __restrict__ a, const T* __restrict__ b, T scale, T* __restrict__ out) {
+  pdl_sync();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = scale * a[i] * b[i];
 }
@@ -1113,6 +1120,7 @@ template void launch_scaled_mul<double>(int64_t, const double*, const double*, d
 template void launch_scaled_mul<float>(int64_t, const float*, const float*, double, float*, cudaStream_t);
 template <class T>
 __global__ void fill_t_kernel(int64_t n, T v, T* __restrict__ x) {
+  pdl_sync();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] = v;
 }
