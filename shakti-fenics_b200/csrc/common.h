@@ -46,7 +46,7 @@ extern int64_t g_kernel_launches;
                                                  cudaGetErrorString(e_)); \
   } while (0)
 
-// Programmatic dependent launch (SHAKTI_PDL=1, experimental): the kernels of the V-cycle are launched with
+// Programmatic dependent launch (default on, SHAKTI_PDL=0 disables): the kernels of the V-cycle are launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization, so the NEXT kernel of the chain is scheduled while the
 // current one drains and blocks in `griddepcontrol.wait` until its predecessor has completed and flushed.
 // Every kernel launched this way calls pdl_sync() before it touches memory; launched normally that is a no-op.

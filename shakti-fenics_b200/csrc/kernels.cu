@@ -13,7 +13,8 @@ namespace shakti {
 int64_t g_kernel_launches = 0;
 
 bool pdl_enabled() {
-  static const bool on = getenv("SHAKTI_PDL") != nullptr && atoi(getenv("SHAKTI_PDL")) != 0;
+  // on by default (measured at C4: -0.6 % of a step on one B200, -2.5 % on eight); SHAKTI_PDL=0 launches plainly
+  static const bool on = getenv("SHAKTI_PDL") == nullptr || atoi(getenv("SHAKTI_PDL")) != 0;
   return on;
 }
 

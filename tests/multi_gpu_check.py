@@ -14,6 +14,56 @@ for p in (str(ROOT), str(ROOT / "shakti-fenics_b200"), str(ROOT / "tests")):
         sys.path.insert(0, p)
 
 
+def solve_md_leg(rank, world):
+    """The reference-shaped entry point solvers.solve(md) on several GPUs: every rank saves its OWNED slice
+    through the asynchronous double-buffered path, rank 0 assembles the (nti, nd) arrays and writes the .npy
+    files, a checkpoint is written by rank 0 from all ranks' entries; the files must equal a plain stepping of
+    the oracle.  Resume on the same number of GPUs continues to the same final fields."""
+    import shutil
+    import tempfile
+    import torch.distributed as dist
+    for p in (ROOT / "shakti-fenics_b200" / "source", ROOT / "shakti-fenics_b200" / "setups"):
+        if str(p) not in sys.path:
+            sys.path.insert(0, str(p))
+    import solvers
+    from _synthetic import md_from_case
+    from common import make_oracle, relinf
+    from shakti_b200 import configs, fem
+    box = [tempfile.mkdtemp(prefix="shakti_mg_") if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    out = Path(box[0]) / "run"
+    nt, nt_save = 8, 2            # nt divisible by nt_save, as every reference setup has it (solvers.py:110)
+
+    def make(nsteps):
+        case = configs.rect_steady(nx=60, ny=40, nsteps=nt)
+        md = md_from_case(fem.comm_world(), case, str(ROOT / "shakti-fenics_b200" / "setups" / "setup_rect250k.py"),
+                          nt_save=nt_save, nt_check=2 * nt_save, results_name=str(out))
+        md.timesteps = case.timesteps[:nsteps]
+        md.resume = True
+        return md, case
+
+    md, case = make(6)           # saves after steps 0, 2, 4; the last checkpoint is the one after step 4
+    solvers.solve(md)
+    md, case = make(nt)          # resumes from the checkpoint and finishes
+    solvers.solve(md)
+    good = True
+    if rank == 0:
+        N, b = np.load(out / "N.npy"), np.load(out / "b.npy")
+        bc = solvers.get_bcs(md)[0].dofs
+        o = make_oracle(case.xy, case.cells, case.fields, bc, case.N_bdry)
+        errs, j = [], 0
+        for i, dt in enumerate(o.dt_schedule(case.timesteps[:nt])):
+            o.step(dt)
+            if i % nt_save == 0 and j < N.shape[0]:
+                errs.append(max(relinf(N[j], o.N), relinf(b[j], o.b)))
+                j += 1
+        good = N.shape == (nt // nt_save, case.n_vert) and j == nt // nt_save and max(errs) < 1e-8
+        print(f"[{world} GPUs, solve(md) with owned-slice async saves + checkpoint/resume] rows {N.shape[0]} max field err "
+              f"{max(errs):.1e}" + ("  OK" if good else "  MISMATCH"), flush=True)
+        shutil.rmtree(box[0], ignore_errors=True)
+    return good
+
+
 def main():
     import torch
     import torch.distributed as dist
@@ -71,6 +121,7 @@ def main():
                   f"{st['amg_levels']} errs " + " ".join(f"{k}={v:.1e}" for k, v in errs.items())
                   + ("  OK" if good else "  MISMATCH"), flush=True)
         m.close()
+    ok &= solve_md_leg(rank, world)
     capi.comm_finalize()
     dist.destroy_process_group()
     if rank == 0:
