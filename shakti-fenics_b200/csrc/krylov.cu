@@ -2,7 +2,6 @@
 #include "krylov.h"
 
 #include <cmath>
-#include <cstdlib>
 
 namespace shakti {
 
@@ -94,36 +93,6 @@ KrylovResult Gmres::solve(const ApplyFn& A, const PrecFn& M, const AllReduceFn& 
       double* zj = Z_.p + (size_t)j * ldz_;
       M(V_.p + (size_t)j * ld_, zj);
       A(zj, w);
-      double hj1;
-      const double* hdev;
-      static const bool cgs1 = getenv("SHAKTI_GMRES_CGS2") == nullptr;
-      if (cgs1) {
-        // Classical Gram-Schmidt ONCE, two passes over the basis: 1. h = V^T w together with <w,w> (w is
-        // stored right behind v_j, so it is simply one more "basis vector" of the fused dot),
-        // 2. v_{j+1} = (w - V h)/||w - V h|| with the norm by Pythagoras.  With a strong right
-        // preconditioner w = A M v_j is close to v_j, so h_j ~ 1 and the remainder is small against w; the
-        // rounding errors that leaves along V are O(eps ||w|| / ||w - V h||) ~ 5-10 eps per step, far below any
-        // tolerance used here over the <= 40 vectors of a cycle.  A remainder below 1 % of w (not seen in
-        // practice) is re-orthogonalised by the two-pass branch below.
-        launch_multi_dot(red_, n_, j + 2, V_.p, ld_, w, h_, s_);
-        allreduce(h_, j + 2);
-        read(h_, j + 2);
-        double s2 = 0.0;
-        for (int i = 0; i <= j; ++i) { hh[i] = hbuf[i]; s2 += hbuf[i] * hbuf[i]; }
-        const double ww = hbuf[j + 1];
-        const double rem = ww - s2;
-        if (rem > 1e-4 * ww) {
-          hj1 = std::sqrt(rem);
-          hdev = h_;
-        } else {
-          hj1 = -1.0;   // severe cancellation: fall through to the re-orthogonalising branch
-          hdev = nullptr;
-        }
-      } else {
-        hj1 = -1.0;
-        hdev = nullptr;
-      }
-      if (hj1 < 0.0) {
       // classical Gram-Schmidt twice (CGS2) in three passes over the basis:
       //   1. h = V^T w                       2. w -= V h fused with h2 = V^T w, <w,w>      3. w = (w - V h2)/||.||
       launch_multi_dot(red_, n_, j + 1, V_.p, ld_, w, h_, s_);
@@ -138,9 +107,8 @@ KrylovResult Gmres::solve(const ApplyFn& A, const PrecFn& M, const AllReduceFn& 
       double s2 = 0.0;
       for (int i = 0; i <= j; ++i) { hh[i] = hbuf[i] + hbuf[m_ + 2 + i]; s2 += hbuf[m_ + 2 + i] * hbuf[m_ + 2 + i]; }
       const double rem = hbuf[m_ + 2 + j + 1] - s2;   // ||w - V h2||^2 by Pythagoras: h2 is tiny, no cancellation
-      hdev = h2_;
-      hj1 = std::sqrt(std::max(rem, 0.0));
-      }
+      const double* hdev = h2_;
+      const double hj1 = std::sqrt(std::max(rem, 0.0));
       // Hessenberg column j, stored rotations, new rotation, residual estimate
       double* col = H.data() + (size_t)j * (m_ + 1);
       for (int i = 0; i <= j; ++i) col[i] = hh[i];
