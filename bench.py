@@ -396,20 +396,23 @@ def main():
                 if r["rows"] == 0:
                     continue
                 gbs = r["bytes"] / 1e9 / (r["ms"] / 1e3)
-                levels.append({"level": lvl, "rows": r["rows"], "nnz": r["nnz"], "us": 1e3 * r["ms"], "algorithmic_GB": r["bytes"] / 1e9,
+                levels.append({"level": lvl, "rows": r["rows"], "nnz": r["nnz"], "value_bytes": r["value_bytes"], "us": 1e3 * r["ms"],
+                               "algorithmic_GB": r["bytes"] / 1e9,
                                "GBps": gbs, "frac": gbs / peak})
         traffic = None
         tf = ROOT / "profiles" / "r2_traffic.json"
         if tf.exists() and world == 1 and not weak:
-            t_ = json.loads(tf.read_text()).get("amg_cheby_fine_fp32", {})
+            t_ = json.loads(tf.read_text()).get("amg_cheby_fine", {})
             if t_.get("nside") == nside:
                 traffic = t_["traffic_bytes"]       # dram read+write per launch, ncu --set full (profiles/)
         if levels:
             l0 = levels[0]
-            roofline = {"bound": "hbm", "kernel": "amg_cheby_kernel<float,1> (AMG smoother, fine level, fp32 SELL-32 copy of J)",
+            kname = ("amg_cheby_h_kernel (AMG smoother, fine level, half-precision row-scaled SELL-32 copy of J, fp32 vectors)"
+                     if l0["value_bytes"] == 2 else "amg_cheby_kernel<float,1> (AMG smoother, fine level, fp32 SELL-32 copy of J)")
+            roofline = {"bound": "hbm", "kernel": kname,
                         "achieved": l0["GBps"], "peak": peak, "unit": "GB/s", "frac": l0["frac"], "traffic": traffic,
                         "algorithmic_bytes": l0["algorithmic_GB"] * 1e9, "peak_source": peak_src, "levels": levels,
-                        "how": "(4+4) nnz + 28 rows algorithmic bytes / mean of 20 launches, CUDA events on the library stream; "
+                        "how": "(value_bytes+4) nnz + 28 rows algorithmic bytes / mean of 20 launches, CUDA events on the library stream; "
                                "matrix >> L2; largest share of the step in profiles/r2_launch_shares_16M_one_step.csv",
                         "secondary": {"spmv_fine_fp64": kern["spmv"], "assemble_blocks": kern["assemble"]}}
         else:

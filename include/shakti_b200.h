@@ -268,10 +268,11 @@ int shakti_debug_copy_bw(void* host, int64_t bytes, int reps, double* h2d_gbs, d
 int shakti_time_kernel(shakti_model* m, int which, int reps, double dt, double* ms_per_launch);
 /* One smoothing step of AMG level `level` (the V-cycle's dominant kernel: SELL SpMV fused with the Chebyshev
  * recurrence, in the cycle's precision), timed the same way.  Returns the level's local rows and stored
- * entries and the bytes per matrix value (4: mixed-precision cycle), from which the caller forms the
- * algorithmic bytes (value_bytes + 4) * nnz + 7 * value_bytes * rows.  Needs a built hierarchy (run a step). */
+ * entries, the bytes per matrix value (2: half-precision row-scaled copy on the large levels, 4: fp32 copy) and
+ * per vector entry, from which the caller forms the algorithmic bytes
+ * (value_bytes + 4) * nnz + 7 * vector_bytes * rows.  Needs a built hierarchy (run a step). */
 int shakti_time_amg_smoother(shakti_model* m, int level, int reps, double* ms_per_launch, int64_t* rows,
-                             int64_t* nnz, int32_t* value_bytes);
+                             int64_t* nnz, int32_t* value_bytes, int32_t* vector_bytes);
 /* Algorithmic bytes per launch of kernel `which` (SURVEY.md §8d formulas). */
 int shakti_kernel_bytes(shakti_model* m, int which, double* bytes);
 

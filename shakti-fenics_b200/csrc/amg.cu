@@ -455,6 +455,55 @@ static void launch_cheby(SellViewT<T> A, const T* dinv, const T* b, const T* x, 
     SHAKTI_LAUNCH_PDL((amg_cheby_kernel<T, 1>), div_up((int64_t)A.n_slices * 32, 256), 256, 0, s, A, dinv, b, x, d, x_out, (T)c1, (T)c2);
 }
 
+// ---- the same two kernels of the LARGE levels on the half-precision, row-scaled copy Ah = D^-1 A (unit
+// diagonal): 6 instead of 8 bytes per stored entry on kernels that are purely bandwidth bound.  The vectors
+// stay fp32 and the products are accumulated in fp32; the 5e-4 relative rounding of the entries perturbs the
+// PRECONDITIONER only (the Krylov operator and the Galerkin products use the fp64 values).
+//   Chebyshev step:  r = dinv b - Ah x ;  d = c1 d + c2 r ;  x_out = x + d
+__global__ void __launch_bounds__(256)
+amg_cheby_h_kernel(int32_t n_rows, int32_t n_slices, const int32_t* __restrict__ slice_ptr, const int32_t* __restrict__ col,
+                   const __half* __restrict__ val, const float* __restrict__ dinv, const float* __restrict__ b,
+                   const float* __restrict__ x, float* __restrict__ d, float* __restrict__ x_out, float c1, float c2) {
+  pdl_sync();
+  const int32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+  const int32_t slice = row >> 5;
+  if (slice >= n_slices) return;
+  const int32_t base = slice_ptr[slice];
+  const int32_t w = (slice_ptr[slice + 1] - base) >> 5;
+  const int32_t* __restrict__ cp = col + base + (row & 31);
+  const __half* __restrict__ vp = val + base + (row & 31);
+  float acc = 0.f;
+#pragma unroll 4
+  for (int k = 0; k < w; ++k) acc += __half2float(vp[32 * k]) * x[cp[32 * k]];
+  if (row >= n_rows) return;
+  const float r = dinv[row] * b[row] - acc;
+  const float dn = c1 * d[row] + c2 * r;
+  d[row] = dn;
+  x_out[row] = x[row] + dn;
+}
+//   residual:  r = b - A x = b - (Ah x) / dinv
+__global__ void __launch_bounds__(256)
+amg_resid_h_kernel(int32_t n_rows, int32_t n_slices, const int32_t* __restrict__ slice_ptr, const int32_t* __restrict__ col,
+                   const __half* __restrict__ val, const float* __restrict__ dinv, const float* __restrict__ b,
+                   const float* __restrict__ x, float* __restrict__ r) {
+  pdl_sync();
+  const int32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+  const int32_t slice = row >> 5;
+  if (slice >= n_slices) return;
+  const int32_t base = slice_ptr[slice];
+  const int32_t w = (slice_ptr[slice + 1] - base) >> 5;
+  const int32_t* __restrict__ cp = col + base + (row & 31);
+  const __half* __restrict__ vp = val + base + (row & 31);
+  float acc = 0.f;
+#pragma unroll 4
+  for (int k = 0; k < w; ++k) acc += __half2float(vp[32 * k]) * x[cp[32 * k]];
+  if (row >= n_rows) return;
+  const float di = dinv[row];
+  r[row] = b[row] - (di != 0.f ? acc / di : 0.f);
+}
+// does level operator A run on its half-precision copy?
+static bool uses_half(const Amg::Impl& I, const DevSell& A);
+
 // first Chebyshev step from a zero guess: d = (dinv b)/theta ; x = d
 template <class T>
 __global__ void amg_cheby_first_kernel(int32_t n, const T* __restrict__ dinv, const T* __restrict__ b, T inv_theta,
@@ -720,15 +769,21 @@ static void numeric_level(Amg::Impl& I, size_t l, const DevSell& Afine, const in
   spgemm_numeric(L.R, L.AP, I.lv[l + 1]->A, L.plan_RAP, s);    // Galerkin: R (A P)
 }
 
+static bool uses_half(const Amg::Impl& I, const DevSell& A) {
+  static const bool off = getenv("SHAKTI_AMG_FP16") != nullptr && atoi(getenv("SHAKTI_AMG_FP16")) == 0;
+  return !off && I.opt.fp32_cycle && I.opt.smoother == 1 && A.n_rows >= kChebyWideRowsBelow;
+}
+
 // Copies the V-cycle reads: smoother diagonal in the cycle's precision and, for the mixed-precision
-// cycle, single-precision values of A, P and R.
+// cycle, single-precision values of A, P and R (half-precision row-scaled values of A on the large levels).
 static void sync_cycle_precision(Amg::Impl& I, size_t l, const DevSell& Afine, bool matrices) {
   cudaStream_t s = I.s;
   AmgLevel& L = *I.lv[l];
   const DevSell& A = (l == 0) ? Afine : L.A;
   if (I.opt.fp32_cycle) {
     launch_d2f(L.n, L.dinv.p, L.vf.dinv.p, s);
-    A.refresh_f32(s);
+    if (uses_half(I, A)) A.refresh_f16_scaled(L.dinv.p, s);
+    else A.refresh_f32(s);
     if (matrices && !L.last) { L.P.refresh_f32(s); L.R.refresh_f32(s); }
   } else if (L.n) {
     SHAKTI_CUDA(cudaMemcpyAsync(L.vd.dinv.p, L.dinv.p, sizeof(double) * L.n, cudaMemcpyDeviceToDevice, s));
@@ -1259,6 +1314,33 @@ void Amg::refresh(const DevSell& Afine, const int32_t* fine_diag_pos) {
   ++refreshes_;
 }
 
+template <class T>
+static void cheby_step(Amg::Impl& I, const DevSell& A, const T* dinv, const T* b, const T* x, T* d, T* x_out, double c1, double c2,
+                       cudaStream_t s) {
+  launch_cheby<T>(view_as<T>(A), dinv, b, x, d, x_out, c1, c2, s);
+}
+template <>
+void cheby_step<float>(Amg::Impl& I, const DevSell& A, const float* dinv, const float* b, const float* x, float* d, float* x_out,
+                       double c1, double c2, cudaStream_t s) {
+  if (uses_half(I, A))
+    SHAKTI_LAUNCH_PDL(amg_cheby_h_kernel, div_up((int64_t)A.n_slices * 32, 256), 256, 0, s, A.n_rows, A.n_slices, A.slice_ptr.p, A.col.p,
+                      A.valh.p, dinv, b, x, d, x_out, (float)c1, (float)c2);
+  else
+    launch_cheby<float>(viewf(A), dinv, b, x, d, x_out, c1, c2, s);
+}
+template <class T>
+static void level_residual(Amg::Impl& I, const DevSell& A, const T* dinv, const T* x, const T* b, T* r, cudaStream_t s) {
+  launch_residual<T>(view_as<T>(A), x, b, r, s);
+}
+template <>
+void level_residual<float>(Amg::Impl& I, const DevSell& A, const float* dinv, const float* x, const float* b, float* r, cudaStream_t s) {
+  if (uses_half(I, A))
+    SHAKTI_LAUNCH_PDL(amg_resid_h_kernel, div_up((int64_t)A.n_slices * 32, 256), 256, 0, s, A.n_rows, A.n_slices, A.slice_ptr.p, A.col.p,
+                      A.valh.p, dinv, b, x, r);
+  else
+    launch_residual<float>(viewf(A), x, b, r, s);
+}
+
 // `sweeps` smoothing steps on A x = b, in place on v.x (ping-pong with v.x2).  zero_guess: v.x is
 // taken as 0 and the first step needs no SpMV.  Every SpMV is preceded by the level's halo exchange
 // unless the caller says the ghosts are already current.
@@ -1289,7 +1371,7 @@ static void smooth(Amg::Impl& I, AmgLevel& L, const DevSell& A, const T* b, int 
         rho = rho_n;
       }
       if (I.opt.smoother_halo && !(ghosts_current && k == k0)) L.halo->exchange(v.x.p, s);
-      if (L.n) launch_cheby<T>(view_as<T>(A), v.dinv.p, b, v.x.p, v.d.p, v.x2.p, c1, c2, s);
+      if (L.n) cheby_step<T>(I, A, v.dinv.p, b, v.x.p, v.d.p, v.x2.p, c1, c2, s);
       std::swap(v.x.p, v.x2.p);
     }
   } else {                      // damped Jacobi
@@ -1352,7 +1434,7 @@ static void vcycle(Amg::Impl& I, const DevSell& Afine) {
     }
     smooth<T>(I, L, A, v.b.p, I.opt.presmooth, true, false);
     L.halo->exchange(v.x.p, s);
-    launch_residual<T>(view_as<T>(A), v.x.p, v.b.p, v.r.p, s);
+    level_residual<T>(I, A, v.dinv.p, v.x.p, v.b.p, v.r.p, s);
     launch_spmv<T>(view_as<T>(L.R), v.r.p, vecs<T>(*I.lv[l + 1]).b.p, s);
   }
   for (int l = nl - 2; l >= 0; --l) {   // upward
@@ -1416,15 +1498,16 @@ static void run_cycle(Amg::Impl& I, const DevSell& Afine) {
   g_kernel_launches += I.graph_launches;
 }
 
-bool Amg::launch_level_smoother(int level, const DevSell& Afine, int64_t* rows, int64_t* nnz) {
+bool Amg::launch_level_smoother(int level, const DevSell& Afine, int64_t* rows, int64_t* nnz, int* value_bytes) {
   Impl& I = *p_;
   if (!I.built || level < 0 || level >= (int)I.lv.size()) return false;
   AmgLevel& L = *I.lv[level];
   const DevSell& A = (level == 0) ? Afine : L.A;
   if (rows) *rows = L.n;
   if (nnz) *nnz = A.nnz;
+  if (value_bytes) *value_bytes = uses_half(I, A) ? 2 : (I.opt.fp32_cycle ? 4 : 8);
   if (L.n == 0) return true;
-  if (I.opt.fp32_cycle) launch_cheby<float>(viewf(A), L.vf.dinv.p, L.vf.b.p, L.vf.x.p, L.vf.d.p, L.vf.x2.p, 0.3, 0.2, I.s);
+  if (I.opt.fp32_cycle) cheby_step<float>(I, A, L.vf.dinv.p, L.vf.b.p, L.vf.x.p, L.vf.d.p, L.vf.x2.p, 0.3, 0.2, I.s);
   else launch_cheby<double>(view(A), L.vd.dinv.p, L.vd.b.p, L.vd.x.p, L.vd.d.p, L.vd.x2.p, 0.3, 0.2, I.s);
   return true;
 }

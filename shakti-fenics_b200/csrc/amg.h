@@ -59,7 +59,7 @@ class Amg {
   bool fp32() const;
   // micro-benchmark hook: one smoothing step (SpMV fused with the Chebyshev recurrence) of level `level` on
   // the cycle's own vectors; rows / stored entries of that level's operator are returned for the roofline
-  bool launch_level_smoother(int level, const DevSell& Afine, int64_t* rows, int64_t* nnz);
+  bool launch_level_smoother(int level, const DevSell& Afine, int64_t* rows, int64_t* nnz, int* value_bytes = nullptr);
   int levels() const;
   double operator_complexity() const;
   int64_t refreshes() const { return refreshes_; }

@@ -1349,13 +1349,14 @@ int shakti_time_kernel(shakti_model* m, int which, int reps, double dt, double* 
 }
 
 int shakti_time_amg_smoother(shakti_model* m, int level, int reps, double* ms_per_launch, int64_t* rows, int64_t* nnz,
-                             int32_t* value_bytes) {
+                             int32_t* value_bytes, int32_t* vector_bytes) {
   SHAKTI_TRY
   SHAKTI_REQUIRE(m && ms_per_launch && reps > 0, "bad arguments");
   use_device(m);
   SHAKTI_REQUIRE(m->amg && m->amg->ready() && m->J_valid, "no AMG hierarchy yet: run a step first");
   int64_t r = 0, z = 0;
-  SHAKTI_REQUIRE(m->amg->launch_level_smoother(level, m->J, &r, &z), "no such AMG level on this rank");
+  int vb = 0;
+  SHAKTI_REQUIRE(m->amg->launch_level_smoother(level, m->J, &r, &z, &vb), "no such AMG level on this rank");
   cudaEvent_t e0, e1;
   SHAKTI_CUDA(cudaEventCreate(&e0));
   SHAKTI_CUDA(cudaEventCreate(&e1));
@@ -1370,7 +1371,8 @@ int shakti_time_amg_smoother(shakti_model* m, int level, int reps, double* ms_pe
   *ms_per_launch = (double)ms / reps;
   if (rows) *rows = r;
   if (nnz) *nnz = z;
-  if (value_bytes) *value_bytes = m->amg->fp32() ? 4 : 8;
+  if (value_bytes) *value_bytes = vb;
+  if (vector_bytes) *vector_bytes = m->amg->fp32() ? 4 : 8;
   SHAKTI_CATCH
 }
 

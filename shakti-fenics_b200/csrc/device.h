@@ -1,5 +1,7 @@
 // Device-side data structures and kernel launch wrappers.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.h"
 #include "prep.h"
 
@@ -24,8 +26,12 @@ struct DevSell {
   DevBuf<int32_t> slice_ptr, col, rowlen;
   DevBuf<double> val;
   mutable DevBuf<float> valf;   // single-precision copy of val (mixed-precision AMG cycle), made on demand
+  mutable DevBuf<__half> valh;  // half-precision copy of D^-1 A (smoother / residual of the large AMG levels)
   void upload_pattern(const HostSell& h, int64_t nnz_);
   void refresh_f32(cudaStream_t s) const;   // valf <- val
+  // valh <- dinv[row] * val: the row-scaled operator has a unit diagonal and off-diagonals of order 1, which is
+  // what makes 16-bit storage possible (raw Jacobian entries span 1e-11 ... 4e-3)
+  void refresh_f16_scaled(const double* dinv, cudaStream_t s) const;
 };
 
 template <class T>

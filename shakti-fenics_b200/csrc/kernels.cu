@@ -1103,6 +1103,21 @@ void launch_f2d(int64_t n, const float* a, double* out, cudaStream_t s) {
   if (n == 0) return;
   SHAKTI_LAUNCH(f2d_kernel, conv_blocks(n), 256, 0, s, n, a, out);
 }
+__global__ void __launch_bounds__(256)
+sell_scale_to_half_kernel(SellView A, const double* __restrict__ dinv, __half* __restrict__ out) {
+  const int32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+  const int32_t slice = row >> 5;
+  if (slice >= A.n_slices) return;
+  const int32_t base = A.slice_ptr[slice] + (row & 31);
+  const int32_t w = (A.slice_ptr[slice + 1] - A.slice_ptr[slice]) >> 5;
+  const double s = row < A.n_rows ? dinv[row] : 0.0;
+  for (int k = 0; k < w; ++k) out[base + 32 * k] = __float2half_rn((float)(s * A.val[base + 32 * k]));
+}
+void DevSell::refresh_f16_scaled(const double* dinv, cudaStream_t s) const {
+  if (valh.n != (size_t)padded) valh.alloc((size_t)std::max<int64_t>(padded, 1));
+  if (n_rows == 0) return;
+  SHAKTI_LAUNCH(sell_scale_to_half_kernel, div_up((int64_t)n_slices * 32, 256), 256, 0, s, view(*this), dinv, valh.p);
+}
 void DevSell::refresh_f32(cudaStream_t s) const {
   if (valf.n != (size_t)padded) valf.alloc((size_t)padded);
   launch_d2f(padded, val.p, valf.p, s);

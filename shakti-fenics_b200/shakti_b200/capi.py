@@ -483,11 +483,11 @@ class Model:
 
     def time_amg_smoother(self, level, reps=20):
         """-> dict(ms, rows, nnz, value_bytes, bytes) for one smoothing step of AMG level `level`."""
-        ms, rows, nnz, vb = C.c_double(0), C.c_int64(0), C.c_int64(0), C.c_int32(0)
+        ms, rows, nnz, vb, xb = C.c_double(0), C.c_int64(0), C.c_int64(0), C.c_int32(0), C.c_int32(0)
         _check(self.lib.shakti_time_amg_smoother(self._h, C.c_int(level), C.c_int(reps), C.byref(ms), C.byref(rows),
-                                                 C.byref(nnz), C.byref(vb)))
-        by = (vb.value + 4) * nnz.value + 7 * vb.value * rows.value
-        return dict(ms=ms.value, rows=rows.value, nnz=nnz.value, value_bytes=vb.value, bytes=by)
+                                                 C.byref(nnz), C.byref(vb), C.byref(xb)))
+        by = (vb.value + 4) * nnz.value + 7 * xb.value * rows.value
+        return dict(ms=ms.value, rows=rows.value, nnz=nnz.value, value_bytes=vb.value, vector_bytes=xb.value, bytes=by)
 
     def kernel_bytes(self, which):
         b = C.c_double(0)
