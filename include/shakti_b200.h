@@ -334,6 +334,10 @@ int shakti_host_mesh_array(shakti_host_mesh* hm, int which, int32_t* out, int64_
  * aggregation of a square CSR matrix, as the AMG set-up does on each level; agg_out[i] in [0, *n_agg) or -1. */
 int shakti_host_amg_aggregate(int32_t n, const int32_t* rowptr, const int32_t* col, const double* val, double theta,
                               const uint8_t* exclude, int32_t* agg_out, int32_t* n_agg);
+/* Host-only self test of the symmetric-heap allocator behind the multi-GPU staging buffers (csrc/comm.cu): a
+ * deterministic sequence of `rounds` allocations / releases on a heap of heap_bytes; *violations counts
+ * misaligned or overlapping blocks, accepted double frees and a heap that does not coalesce back to one block. */
+int shakti_host_heap_selftest(int64_t heap_bytes, int32_t rounds, int32_t* violations);
 /* info[0..5] = n_owned, n_local, n_cell_local, nnz_local, padded SELL entries, n_nbrs */
 int shakti_host_mesh_info(shakti_host_mesh* hm, int64_t info[6]);
 

@@ -1391,6 +1391,12 @@ int shakti_comm_finalize(void) {
   comm_finalize();
   SHAKTI_CATCH
 }
+int shakti_host_heap_selftest(int64_t heap_bytes, int32_t rounds, int32_t* violations) {
+  SHAKTI_TRY
+  SHAKTI_REQUIRE(heap_bytes >= 4096 && rounds > 0 && violations, "bad arguments");
+  *violations = heap_selftest((size_t)heap_bytes, rounds);
+  SHAKTI_CATCH
+}
 int shakti_get_owned(shakti_model* m, int32_t* ids, int64_t* n_owned) {
   SHAKTI_TRY
   SHAKTI_REQUIRE(m && n_owned, "null argument");

@@ -94,35 +94,78 @@ struct P2pState {
 static P2pState g_p2p;
 static P2pGather* g_ar = nullptr;    // the small all-reduce (Krylov dots, norms, spectrum bounds)
 
-size_t p2p_alloc(size_t bytes) {
-  SHAKTI_REQUIRE(g_comm.p2p, "p2p_alloc without a symmetric heap");
+// first-fit with splitting; SIZE_MAX when nothing fits
+static size_t heap_take(std::vector<HeapBlock>& bl, size_t bytes) {
   bytes = (std::max<size_t>(bytes, 1) + 255) & ~(size_t)255;
-  for (size_t i = 0; i < g_p2p.blocks.size(); ++i) {
-    HeapBlock& b = g_p2p.blocks[i];
+  for (size_t i = 0; i < bl.size(); ++i) {
+    HeapBlock& b = bl[i];
     if (!b.free || b.size < bytes) continue;
     const size_t off = b.off;
     if (b.size > bytes) {
       const HeapBlock rest{b.off + bytes, b.size - bytes, true};
       b.size = bytes;
       b.free = false;
-      g_p2p.blocks.insert(g_p2p.blocks.begin() + i + 1, rest);
+      bl.insert(bl.begin() + i + 1, rest);
     } else {
       b.free = false;
     }
     return off;
   }
-  throw Error(SHAKTI_ERR_COMM, "symmetric heap exhausted (" + std::to_string(g_p2p.bytes >> 20) +
-                                   " MiB): raise SHAKTI_P2P_HEAP_MB");
+  return (size_t)-1;
 }
-void p2p_free(size_t off) {
-  auto& bl = g_p2p.blocks;
+// release with coalescing of free neighbours; false when `off` is not an allocated block
+static bool heap_give(std::vector<HeapBlock>& bl, size_t off) {
   for (size_t i = 0; i < bl.size(); ++i) {
     if (bl[i].off != off || bl[i].free) continue;
     bl[i].free = true;
     if (i + 1 < bl.size() && bl[i + 1].free) { bl[i].size += bl[i + 1].size; bl.erase(bl.begin() + i + 1); }
     if (i > 0 && bl[i - 1].free) { bl[i - 1].size += bl[i].size; bl.erase(bl.begin() + i); }
-    return;
+    return true;
   }
+  return false;
+}
+size_t p2p_alloc(size_t bytes) {
+  SHAKTI_REQUIRE(g_comm.p2p, "p2p_alloc without a symmetric heap");
+  const size_t off = heap_take(g_p2p.blocks, bytes);
+  if (off == (size_t)-1)
+    throw Error(SHAKTI_ERR_COMM, "symmetric heap exhausted (" + std::to_string(g_p2p.bytes >> 20) +
+                                     " MiB): raise SHAKTI_P2P_HEAP_MB");
+  return off;
+}
+void p2p_free(size_t off) { heap_give(g_p2p.blocks, off); }
+
+// host-only self test of the heap allocator (no device needed): a deterministic pseudo-random sequence of
+// allocations and releases on a heap of `heap_bytes`; checks alignment, that live blocks never overlap, that
+// releasing everything leaves one free block again.  Returns the number of violations.
+int heap_selftest(size_t heap_bytes, int rounds) {
+  std::vector<HeapBlock> bl(1, HeapBlock{0, heap_bytes, true});
+  std::vector<std::pair<size_t, size_t>> live;   // (offset, requested bytes)
+  unsigned long long rng = 88172645463325252ULL;
+  auto next = [&]() { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; return rng; };
+  int bad = 0;
+  for (int r = 0; r < rounds; ++r) {
+    if (live.empty() || next() % 3 != 0) {
+      const size_t want = 1 + next() % (heap_bytes / 16);
+      const size_t off = heap_take(bl, want);
+      if (off == (size_t)-1) continue;             // full: fine
+      if (off % 256 != 0 || off + want > heap_bytes) ++bad;
+      for (const auto& l : live) {
+        const size_t a0 = l.first, a1 = l.first + ((l.second + 255) & ~(size_t)255);
+        const size_t b0 = off, b1 = off + ((want + 255) & ~(size_t)255);
+        if (a0 < b1 && b0 < a1) ++bad;
+      }
+      live.push_back({off, want});
+    } else {
+      const size_t k = next() % live.size();
+      if (!heap_give(bl, live[k].first)) ++bad;
+      if (heap_give(bl, live[k].first)) ++bad;     // double free must be refused
+      live.erase(live.begin() + k);
+    }
+  }
+  for (const auto& l : live)
+    if (!heap_give(bl, l.first)) ++bad;
+  if (bl.size() != 1 || !bl[0].free || bl[0].off != 0 || bl[0].size != heap_bytes) ++bad;
+  return bad;
 }
 char* p2p_local(size_t off) { return g_p2p.heap + off; }
 char* p2p_peer(int rank, size_t off) { return g_p2p.peer[rank] + off; }

@@ -28,6 +28,7 @@ size_t p2p_alloc(size_t bytes);            // 256-byte aligned offset; throws wh
 void p2p_free(size_t off);
 char* p2p_local(size_t off);
 char* p2p_peer(int rank, size_t off);
+int heap_selftest(size_t heap_bytes, int rounds);   // host-only check of the allocator (tests)
 int p2p_error();                           // != 0 after a kernel-side wait timed out (checked at host syncs)
 // host-level allgather of k doubles per rank (set-up phases): out[r*k + i]
 std::vector<double> comm_host_allgather_k(const double* v, int k, cudaStream_t s);

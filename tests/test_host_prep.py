@@ -224,3 +224,14 @@ def test_assembly_row_block_plan_emulated_in_numpy(mesh, nranks):
         own = l2g[: hm.n_owned]
         assert np.allclose(F, Fref[own], rtol=1e-13, atol=1e-13)
         assert abs(_sell_to_csr(hm, vals, nv)[own] - Jref[own]).max() < 1e-12
+
+
+def test_symmetric_heap_allocator_selftest():
+    """The first-fit allocator that places halo staging slots and flags in the peer-mapped heap (csrc/comm.cu):
+    alignment, no overlap of live blocks, double frees refused, full coalescing -- host logic, no GPU needed."""
+    import ctypes as C
+    lib = capi.load()
+    for heap, rounds in ((1 << 20, 4000), (256 << 20, 20000), (4096, 200)):
+        bad = C.c_int32(-1)
+        assert lib.shakti_host_heap_selftest(C.c_int64(heap), C.c_int32(rounds), C.byref(bad)) == 0
+        assert bad.value == 0, (heap, rounds, bad.value)
