@@ -3,10 +3,59 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <functional>
 #include <numeric>
 #include <stdexcept>
+#include <thread>
 
 namespace shakti {
+
+// ------------------------------------------------------------------ host threads
+// The preprocessing is embarrassingly parallel over rows / cells / blocks; it runs once per model but on
+// 16M-dof meshes one thread needs ~15 s.  SHAKTI_HOST_THREADS overrides the default (hardware threads, at
+// most 16, divided among the ranks of a multi-GPU job: they all preprocess at the same time).
+static int g_host_thread_share = 1;
+static int host_threads() {
+  if (const char* e = getenv("SHAKTI_HOST_THREADS")) return std::max(1, atoi(e));
+  const int hw = (int)std::thread::hardware_concurrency();
+  return std::max(1, std::min(16, hw > 0 ? hw / std::max(1, g_host_thread_share) : 1));
+}
+// fn(begin, end, thread index) over [0, n) in contiguous chunks
+template <class F>
+static void parallel_for(int64_t n, F fn, int64_t min_per_thread = 4096) {
+  const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(host_threads(), n / std::max<int64_t>(min_per_thread, 1)));
+  if (nt <= 1) { fn((int64_t)0, n, 0); return; }
+  std::vector<std::thread> th;
+  std::vector<std::exception_ptr> err(nt);
+  for (int t = 0; t < nt; ++t)
+    th.emplace_back([&, t]() {
+      try { fn(n * t / nt, n * (t + 1) / nt, t); } catch (...) { err[t] = std::current_exception(); }
+    });
+  for (auto& x : th) x.join();
+  for (auto& e : err)
+    if (e) std::rethrow_exception(e);
+}
+// stable parallel sort: sorted chunks, then pairwise stable merges
+template <class It, class Cmp>
+static void parallel_stable_sort(It first, It last, Cmp cmp) {
+  const int64_t n = last - first;
+  int nt = (int)std::max<int64_t>(1, std::min<int64_t>(host_threads(), n / 65536));
+  if (nt <= 1) { std::stable_sort(first, last, cmp); return; }
+  std::vector<int64_t> cut(nt + 1);
+  for (int t = 0; t <= nt; ++t) cut[t] = n * t / nt;
+  parallel_for(nt, [&](int64_t a, int64_t b, int) { for (int64_t t = a; t < b; ++t) std::stable_sort(first + cut[t], first + cut[t + 1], cmp); }, 1);
+  while (cut.size() > 2) {
+    const size_t pairs = (cut.size() - 1) / 2;
+    parallel_for((int64_t)pairs, [&](int64_t a, int64_t b, int) {
+      for (int64_t k = a; k < b; ++k) std::inplace_merge(first + cut[2 * k], first + cut[2 * k + 1], first + cut[2 * k + 2], cmp);
+    }, 1);
+    std::vector<int64_t> next;
+    for (size_t k = 0; k < cut.size(); k += 2) next.push_back(cut[k]);
+    if (next.back() != n) next.push_back(n);
+    cut.swap(next);
+  }
+}
 
 // ------------------------------------------------------------------ generic sparse helpers
 
@@ -28,19 +77,21 @@ HostSell sell_from_csr(const HostCsr& a) {
   }
   s.slice_ptr[s.n_slices] = (int32_t)off;
   s.col.resize(off);
-  for (int64_t sl = 0; sl < s.n_slices; ++sl) {
-    int w = (s.slice_ptr[sl + 1] - s.slice_ptr[sl]) / 32;
-    for (int lane = 0; lane < 32; ++lane) {
-      int64_t r = sl * 32 + lane;
-      int32_t padcol = (int32_t)std::min<int64_t>(std::min<int64_t>(r, a.n_rows - 1), a.n_cols - 1);
-      if (padcol < 0) padcol = 0;
-      for (int k = 0; k < w; ++k) {
-        int64_t p = (int64_t)s.slice_ptr[sl] + 32 * (int64_t)k + lane;
-        if (r < a.n_rows && k < s.rowlen[r]) s.col[p] = a.col[a.rowptr[r] + k];
-        else s.col[p] = padcol;
+  parallel_for(s.n_slices, [&](int64_t s0, int64_t s1, int) {
+    for (int64_t sl = s0; sl < s1; ++sl) {
+      int w = (s.slice_ptr[sl + 1] - s.slice_ptr[sl]) / 32;
+      for (int lane = 0; lane < 32; ++lane) {
+        int64_t r = sl * 32 + lane;
+        int32_t padcol = (int32_t)std::min<int64_t>(std::min<int64_t>(r, a.n_rows - 1), a.n_cols - 1);
+        if (padcol < 0) padcol = 0;
+        for (int k = 0; k < w; ++k) {
+          int64_t p = (int64_t)s.slice_ptr[sl] + 32 * (int64_t)k + lane;
+          if (r < a.n_rows && k < s.rowlen[r]) s.col[p] = a.col[a.rowptr[r] + k];
+          else s.col[p] = padcol;
+        }
       }
     }
-  }
+  }, 256);
   return s;
 }
 
@@ -119,16 +170,21 @@ static HostCsr adjacency(int64_t n_rows, int64_t n_cols, int64_t ne, const int32
 // finish: replace the trailing -1 of each row by diag id, sort, unique, compact
 static void finish_rows(HostCsr& a, const std::vector<int32_t>& diag_id) {
   int64_t n = a.n_rows;
-  std::vector<int32_t> newptr(n + 1, 0);
+  std::vector<int32_t> newptr(n + 1, 0), len(n, 0);
+  parallel_for(n, [&](int64_t r0, int64_t r1, int) {
+    for (int64_t r = r0; r < r1; ++r) {
+      int32_t* b = a.col.data() + a.rowptr[r];
+      int32_t* e = a.col.data() + a.rowptr[r + 1];
+      *(e - 1) = diag_id[r];
+      std::sort(b, e);
+      len[r] = (int32_t)(std::unique(b, e) - b);
+    }
+  });
   int64_t w = 0;
   for (int64_t r = 0; r < n; ++r) {
-    int32_t* b = a.col.data() + a.rowptr[r];
-    int32_t* e = a.col.data() + a.rowptr[r + 1];
-    *(e - 1) = diag_id[r];
-    std::sort(b, e);
-    e = std::unique(b, e);
+    const int32_t* b = a.col.data() + a.rowptr[r];
     newptr[r] = (int32_t)w;
-    for (int32_t* p = b; p < e; ++p) a.col[w++] = *p;  // w <= position of b, safe in place
+    for (int32_t k = 0; k < len[r]; ++k) a.col[w++] = b[k];  // w <= position of b, safe in place
   }
   newptr[n] = (int32_t)w;
   a.col.resize(w);
@@ -194,82 +250,104 @@ void build_assembly_blocks(const HostMesh& m, int32_t max_cells_per_block, Assem
         if (r < no) vinc[fill[r]++] = e * 4 + a;
       }
   }
-  std::vector<int32_t> stamp(ne, -1), lidx(ne, 0);
+  // Blocks are independent: threads take contiguous runs of blocks, collect their variable-length lists
+  // locally and the runs are concatenated in block order afterwards (same arrays as a serial pass).
+  struct Part {
+    std::vector<int32_t> elems, halo, ecount, hcount, rowinc;   // per block: #cells, #halo vertices; per row: #incident cells
+    std::vector<uint16_t> lv, inc;
+    int32_t max_cells = 0, max_verts = 0;
+    bool fits = true, manifold = true;
+  };
   for (int32_t rb : {256, 128, 64, 32}) {
     out = AssemblyBlocks();
-    std::fill(stamp.begin(), stamp.end(), -1);
     out.rows_per_block = rb;
     out.n_blocks = (no + rb - 1) / rb;
-    out.blk_eptr.assign(out.n_blocks + 1, 0);
-    out.blk_hptr.assign(out.n_blocks + 1, 0);
-    out.inc_ptr.assign(no + 1, 0);
-    out.inc_code.clear();
     out.src.assign(m.S.padded(), 0xFFFFFFFFu);
-    bool fits = true, manifold = true;
-    std::vector<int32_t> elems, halo;
-    for (int32_t B = 0; B < out.n_blocks && fits; ++B) {
-      const int32_t r0 = B * rb, r1 = std::min(no, r0 + rb);
-      elems.clear();
-      for (int32_t r = r0; r < r1; ++r)
-        for (int32_t k = vptr[r]; k < vptr[r + 1]; ++k) {
-          const int32_t e = vinc[k] >> 2;
-          if (stamp[e] != B) { stamp[e] = B; elems.push_back(e); }
-        }
-      std::sort(elems.begin(), elems.end());
-      if ((int32_t)elems.size() > max_cells_per_block || elems.size() >= 4096) { fits = false; break; }
-      for (size_t i = 0; i < elems.size(); ++i) lidx[elems[i]] = (int32_t)i;
-      out.max_cells = std::max<int32_t>(out.max_cells, (int32_t)elems.size());
-      out.blk_elems.insert(out.blk_elems.end(), elems.begin(), elems.end());
-      out.blk_eptr[B + 1] = (int32_t)out.blk_elems.size();
-      // vertices of the block: its own rows first, then the other vertices of its cells (ascending)
-      halo.clear();
-      for (int32_t e : elems)
-        for (int a = 0; a < 3; ++a) {
-          const int32_t v = m.cells[3 * (size_t)e + a];
-          if (v < r0 || v >= r1) halo.push_back(v);
-        }
-      std::sort(halo.begin(), halo.end());
-      halo.erase(std::unique(halo.begin(), halo.end()), halo.end());
-      if ((size_t)(r1 - r0) + halo.size() >= 65535) { fits = false; break; }
-      out.max_verts = std::max<int32_t>(out.max_verts, (int32_t)((r1 - r0) + halo.size()));
-      for (int32_t e : elems)
-        for (int a = 0; a < 3; ++a) {
-          const int32_t v = m.cells[3 * (size_t)e + a];
-          uint16_t lv;
-          if (v >= r0 && v < r1) lv = (uint16_t)(v - r0);
-          else lv = (uint16_t)((r1 - r0) + (std::lower_bound(halo.begin(), halo.end(), v) - halo.begin()));
-          out.blk_lv.push_back(lv);
-        }
-      out.blk_halo.insert(out.blk_halo.end(), halo.begin(), halo.end());
-      out.blk_hptr[B + 1] = (int32_t)out.blk_halo.size();
-      for (int32_t r = r0; r < r1; ++r) {
-        for (int32_t k = vptr[r]; k < vptr[r + 1]; ++k)
-          out.inc_code.push_back((uint16_t)(lidx[vinc[k] >> 2] * 4 + (vinc[k] & 3)));
-        out.inc_ptr[r + 1] = (int32_t)out.inc_code.size();
-        // Jacobian entries of row r
-        for (int32_t kk = m.A.rowptr[r]; kk < m.A.rowptr[r + 1]; ++kk) {
-          const int32_t c = m.A.col[kk];
-          const int64_t p = m.S.pos(r, kk - m.A.rowptr[r]);
-          if (c == r) { out.src[p] = 0xFFFEFFFEu; continue; }
-          uint32_t codes[2] = {0xFFFFu, 0xFFFFu};
-          int found = 0;
-          for (int32_t k = vptr[r]; k < vptr[r + 1]; ++k) {
-            const int32_t e = vinc[k] >> 2, a = vinc[k] & 3;
-            for (int b = 0; b < 3; ++b)
-              if (m.cells[3 * (size_t)e + b] == c) {
-                if (found < 2) codes[found] = (uint32_t)(lidx[e] * 16 + 3 * a + b);
-                ++found;
-              }
+    const int nt_max = host_threads();
+    std::vector<Part> parts(std::max(1, nt_max));
+    int nt_used = 1;
+    parallel_for(out.n_blocks, [&](int64_t B0, int64_t B1, int t) {
+      Part& P = parts[t];
+      std::vector<int32_t> elems, halo;
+      for (int64_t B = B0; B < B1 && P.fits; ++B) {
+        const int32_t r0 = (int32_t)B * rb, r1 = std::min(no, r0 + rb);
+        elems.clear();
+        for (int32_t r = r0; r < r1; ++r)
+          for (int32_t k = vptr[r]; k < vptr[r + 1]; ++k) elems.push_back(vinc[k] >> 2);
+        std::sort(elems.begin(), elems.end());
+        elems.erase(std::unique(elems.begin(), elems.end()), elems.end());
+        if ((int32_t)elems.size() > max_cells_per_block || elems.size() >= 4096) { P.fits = false; break; }
+        auto lidx = [&](int32_t e) { return (int32_t)(std::lower_bound(elems.begin(), elems.end(), e) - elems.begin()); };
+        P.max_cells = std::max<int32_t>(P.max_cells, (int32_t)elems.size());
+        P.elems.insert(P.elems.end(), elems.begin(), elems.end());
+        P.ecount.push_back((int32_t)elems.size());
+        // vertices of the block: its own rows first, then the other vertices of its cells (ascending)
+        halo.clear();
+        for (int32_t e : elems)
+          for (int a = 0; a < 3; ++a) {
+            const int32_t v = m.cells[3 * (size_t)e + a];
+            if (v < r0 || v >= r1) halo.push_back(v);
           }
-          if (found > 2) manifold = false;
-          out.src[p] = codes[0] | (codes[1] << 16);
+        std::sort(halo.begin(), halo.end());
+        halo.erase(std::unique(halo.begin(), halo.end()), halo.end());
+        if ((size_t)(r1 - r0) + halo.size() >= 65535) { P.fits = false; break; }
+        P.max_verts = std::max<int32_t>(P.max_verts, (int32_t)((r1 - r0) + halo.size()));
+        for (int32_t e : elems)
+          for (int a = 0; a < 3; ++a) {
+            const int32_t v = m.cells[3 * (size_t)e + a];
+            uint16_t lv;
+            if (v >= r0 && v < r1) lv = (uint16_t)(v - r0);
+            else lv = (uint16_t)((r1 - r0) + (std::lower_bound(halo.begin(), halo.end(), v) - halo.begin()));
+            P.lv.push_back(lv);
+          }
+        P.halo.insert(P.halo.end(), halo.begin(), halo.end());
+        P.hcount.push_back((int32_t)halo.size());
+        for (int32_t r = r0; r < r1; ++r) {
+          for (int32_t k = vptr[r]; k < vptr[r + 1]; ++k)
+            P.inc.push_back((uint16_t)(lidx(vinc[k] >> 2) * 4 + (vinc[k] & 3)));
+          P.rowinc.push_back(vptr[r + 1] - vptr[r]);
+          // Jacobian entries of row r (positions belong to this row alone: written in place)
+          for (int32_t kk = m.A.rowptr[r]; kk < m.A.rowptr[r + 1]; ++kk) {
+            const int32_t c = m.A.col[kk];
+            const int64_t p = m.S.pos(r, kk - m.A.rowptr[r]);
+            if (c == r) { out.src[p] = 0xFFFEFFFEu; continue; }
+            uint32_t codes[2] = {0xFFFFu, 0xFFFFu};
+            int found = 0;
+            for (int32_t k = vptr[r]; k < vptr[r + 1]; ++k) {
+              const int32_t e = vinc[k] >> 2, a = vinc[k] & 3;
+              for (int bb = 0; bb < 3; ++bb)
+                if (m.cells[3 * (size_t)e + bb] == c) {
+                  if (found < 2) codes[found] = (uint32_t)(lidx(e) * 16 + 3 * a + bb);
+                  ++found;
+                }
+            }
+            if (found > 2) P.manifold = false;
+            out.src[p] = codes[0] | (codes[1] << 16);
+          }
         }
       }
+      (void)nt_used;
+    }, 8);
+    bool fits = true, manifold = true;
+    for (const Part& P : parts) { fits &= P.fits; manifold &= P.manifold; }
+    if (!fits) continue;
+    // concatenate the runs (threads hold ascending, contiguous block ranges)
+    out.blk_eptr.assign(1, 0);
+    out.blk_hptr.assign(1, 0);
+    out.inc_ptr.assign(1, 0);
+    for (const Part& P : parts) {
+      out.max_cells = std::max(out.max_cells, P.max_cells);
+      out.max_verts = std::max(out.max_verts, P.max_verts);
+      out.blk_elems.insert(out.blk_elems.end(), P.elems.begin(), P.elems.end());
+      out.blk_lv.insert(out.blk_lv.end(), P.lv.begin(), P.lv.end());
+      out.blk_halo.insert(out.blk_halo.end(), P.halo.begin(), P.halo.end());
+      out.inc_code.insert(out.inc_code.end(), P.inc.begin(), P.inc.end());
+      for (int32_t c : P.ecount) out.blk_eptr.push_back(out.blk_eptr.back() + c);
+      for (int32_t c : P.hcount) out.blk_hptr.push_back(out.blk_hptr.back() + c);
+      for (int32_t c : P.rowinc) out.inc_ptr.push_back(out.inc_ptr.back() + c);
     }
-    if (fits) {
-      out.ok = manifold;
-      return;
-    }
+    out.ok = manifold;
+    return;
   }
   out.ok = false;
 }
@@ -297,12 +375,15 @@ static std::vector<int32_t> morton_order(int64_t nv, const double* xy) {
   if (!(ext > 0)) ext = 1.0;
   const double scale = (double)((1 << 20) - 1) / ext;
   std::vector<std::pair<uint64_t, int32_t>> key(nv);
-  for (int64_t i = 0; i < nv; ++i) {
-    uint64_t qx = (uint64_t)((xy[2 * i] - xmin) * scale);
-    uint64_t qy = (uint64_t)((xy[2 * i + 1] - ymin) * scale);
-    key[i] = {spread_bits(qx) | (spread_bits(qy) << 1), (int32_t)i};
-  }
-  std::sort(key.begin(), key.end());
+  parallel_for(nv, [&](int64_t a, int64_t b, int) {
+    for (int64_t i = a; i < b; ++i) {
+      uint64_t qx = (uint64_t)((xy[2 * i] - xmin) * scale);
+      uint64_t qy = (uint64_t)((xy[2 * i + 1] - ymin) * scale);
+      key[i] = {spread_bits(qx) | (spread_bits(qy) << 1), (int32_t)i};
+    }
+  });
+  // (key, vertex id) pairs are all distinct, so the order is the same whichever sort produces it
+  parallel_stable_sort(key.begin(), key.end(), [](const std::pair<uint64_t, int32_t>& p, const std::pair<uint64_t, int32_t>& q) { return p < q; });
   std::vector<int32_t> order(nv);
   for (int64_t i = 0; i < nv; ++i) order[i] = key[i].second;
   return order;
@@ -317,6 +398,7 @@ void build_host_mesh(int64_t nv, int64_t ne, const double* xy, const int32_t* ce
   for (int64_t i = 0; i < 3 * ne; ++i)
     if (cells[i] < 0 || cells[i] >= nv) throw std::runtime_error("cell vertex id out of range");
   m.nv_g = nv; m.ne_g = ne; m.rank = rank; m.nranks = nranks;
+  g_host_thread_share = std::max(1, nranks);
   std::vector<int32_t> order;
   if (reorder) order = morton_order(nv, xy);
   else { order.resize(nv); std::iota(order.begin(), order.end(), 0); }
@@ -367,7 +449,7 @@ void build_host_mesh(int64_t nv, int64_t ne, const double* xy, const int32_t* ce
       const int32_t* c = cells + 3 * (int64_t)lc[k];
       key[k] = {std::min(m.g2l[c[0]], std::min(m.g2l[c[1]], m.g2l[c[2]])), lc[k]};
     }
-    if (reorder) std::stable_sort(key.begin(), key.end(), [](auto& a, auto& b) { return a.first < b.first; });
+    if (reorder) parallel_stable_sort(key.begin(), key.end(), [](const std::pair<int32_t, int32_t>& a, const std::pair<int32_t, int32_t>& b) { return a.first < b.first; });
     m.cell_l2g.resize(m.ne);
     m.cells.resize(3 * (size_t)m.ne);
     for (int32_t k = 0; k < m.ne; ++k) {
@@ -396,14 +478,18 @@ void build_host_mesh(int64_t nv, int64_t ne, const double* xy, const int32_t* ce
     const int32_t* p = std::lower_bound(b, e, c);
     return (int32_t)m.S.pos(r, (int)(p - b));
   };
-  for (int32_t e = 0; e < m.ne; ++e)
-    for (int a = 0; a < 3; ++a) {
-      int32_t r = m.cells[3 * (size_t)e + a];
-      if (r >= no) continue;
-      for (int b = 0; b < 3; ++b) m.slot[(size_t)(3 * a + b) * m.ne + e] = find(r, m.cells[3 * (size_t)e + b]);
-    }
+  parallel_for(m.ne, [&](int64_t e0, int64_t e1, int) {
+    for (int64_t e = e0; e < e1; ++e)
+      for (int a = 0; a < 3; ++a) {
+        int32_t r = m.cells[3 * (size_t)e + a];
+        if (r >= no) continue;
+        for (int b = 0; b < 3; ++b) m.slot[(size_t)(3 * a + b) * m.ne + e] = find(r, m.cells[3 * (size_t)e + b]);
+      }
+  });
   m.diag_pos.resize(no);
-  for (int32_t r = 0; r < no; ++r) m.diag_pos[r] = find(r, r);
+  parallel_for(no, [&](int64_t r0, int64_t r1, int) {
+    for (int64_t r = r0; r < r1; ++r) m.diag_pos[r] = find((int32_t)r, (int32_t)r);
+  });
   // winning cell: highest caller cell id containing the vertex
   m.win_cell.assign(no, -1);
   std::vector<int32_t> win_local(no, -1);
