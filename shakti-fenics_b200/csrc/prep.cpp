@@ -302,9 +302,13 @@ void build_assembly_blocks(const HostMesh& m, int32_t max_cells_per_block, Assem
           }
         P.halo.insert(P.halo.end(), halo.begin(), halo.end());
         P.hcount.push_back((int32_t)halo.size());
+        std::vector<int32_t> loc;   // block-local index of each incident cell of the current row
         for (int32_t r = r0; r < r1; ++r) {
-          for (int32_t k = vptr[r]; k < vptr[r + 1]; ++k)
-            P.inc.push_back((uint16_t)(lidx(vinc[k] >> 2) * 4 + (vinc[k] & 3)));
+          loc.clear();
+          for (int32_t k = vptr[r]; k < vptr[r + 1]; ++k) {
+            loc.push_back(lidx(vinc[k] >> 2));
+            P.inc.push_back((uint16_t)(loc.back() * 4 + (vinc[k] & 3)));
+          }
           P.rowinc.push_back(vptr[r + 1] - vptr[r]);
           // Jacobian entries of row r (positions belong to this row alone: written in place)
           for (int32_t kk = m.A.rowptr[r]; kk < m.A.rowptr[r + 1]; ++kk) {
@@ -317,7 +321,7 @@ void build_assembly_blocks(const HostMesh& m, int32_t max_cells_per_block, Assem
               const int32_t e = vinc[k] >> 2, a = vinc[k] & 3;
               for (int bb = 0; bb < 3; ++bb)
                 if (m.cells[3 * (size_t)e + bb] == c) {
-                  if (found < 2) codes[found] = (uint32_t)(lidx(e) * 16 + 3 * a + bb);
+                  if (found < 2) codes[found] = (uint32_t)(loc[k - vptr[r]] * 16 + 3 * a + bb);
                   ++found;
                 }
             }
