@@ -52,6 +52,8 @@ def parse():
                     help="mesh side of the bounded CPU sample (default: sized so that the CPU run takes ~2 minutes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-variant", default="both", choices=["both", "h2d", "d2h", "none"],
+                    help="diagnostic: which host copies the end-to-end leg performs")
     ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel roofline timings")
     return ap.parse_args()
 
@@ -361,9 +363,11 @@ def main():
         barrier()
         t0 = time.perf_counter()
         chk = 0.0
+        use_in, use_out = args.e2e_variant in ("both", "h2d"), args.e2e_variant in ("both", "d2h")
         for i in range(args.steps):
             bufs = out_sets[i % 2]
-            m.step_host_async(dts[k0 + i], pinned_in[i].array.ctypes.data, *[b.array.ctypes.data for b in bufs], owned_only=True)
+            m.step_host_async(dts[k0 + i], pinned_in[i].array.ctypes.data if use_in else None,
+                              *([b.array.ctypes.data for b in bufs] if use_out else [None] * 4), owned_only=True)
             if i >= 1:                       # read the PREVIOUS step's result on the host while this one's copies fly
                 chk += float(out_sets[(i - 1) % 2][1].array[0])
         m.wait_outputs()
@@ -373,7 +377,8 @@ def main():
         e2e = {"value": args.steps / el, "unit": UNIT, "h2d_bytes_per_step": 8 * nv, "d2h_bytes_per_step": 4 * 8 * nv,
                "how": "shakti_step_host_async: per step the forcing H2D and b,N,qx,qy D2H (nt_save=1) through pinned host "
                       "buffers, every rank moving its owned slice; D2H double-buffered behind the next step; wall clock incl. "
-                      "the last copy, max over ranks", "checksum": chk}
+                      "the last copy, max over ranks", "checksum": chk, "variant": args.e2e_variant,
+               "its_e2e": (m.stats()["linear_its"] - st1["linear_its"]) / args.steps}
 
     # ---- rooflines, live CUDA events on the library stream.  Dominant kernel of the step (largest share
     # in profiles/r2_launch_shares_*.csv): the AMG smoother amg_cheby_kernel on the fine level.
