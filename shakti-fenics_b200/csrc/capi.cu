@@ -167,6 +167,8 @@ static double norm2(shakti_model* m, const double* v) {
   allreduce(m, m->scal.p, 1);
   launch_readback(m->scal.p, m->host_scal, 1, m->stream);
   SHAKTI_CUDA(cudaStreamSynchronize(m->stream));
+  if (comm().p2p && p2p_error())
+    throw Error(SHAKTI_ERR_COMM, "a peer-to-peer wait timed out (a rank of the job stopped responding)");
   return std::sqrt(std::max(m->host_scal[0], 0.0));
 }
 
