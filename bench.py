@@ -151,12 +151,13 @@ def cpu_oracle_rate(nside, steps, warmup, target_dofs):
     dts = case.dts(steps + warmup)
     for dt in dts[:warmup]:
         o.step(dt)
-    t0 = time.perf_counter()
+    t0, c0 = time.perf_counter(), time.process_time()
     its = [o.step(dt)[0] for dt in dts[warmup:]]
-    el = time.perf_counter() - t0
+    el, cpu = time.perf_counter() - t0, time.process_time() - c0
     raw = steps / el
     scaled = raw * (case.n_vert / float(target_dofs))
-    sample = (f"{steps} oracle steps (numpy assembly + scipy SuperLU) on a {nside}x{nside}-vertex C4 mesh "
+    sample = (f"{steps} oracle steps (numpy assembly + scipy SuperLU; BLAS pool of {cpu_threads()} threads, measured CPU time / wall "
+              f"time = {cpu / el:.1f} cores busy) on a {nside}x{nside}-vertex C4 mesh "
               f"({case.n_vert} dofs, {np.mean(its):.1f} Newton its/step): {raw:.4g} steps/s measured; `value` is that rate "
               f"EXTRAPOLATED by the dofs ratio {case.n_vert}/{target_dofs} (linear, optimistic for LU)")
     return scaled, raw, sample, el
