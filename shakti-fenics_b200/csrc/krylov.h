@@ -1,4 +1,6 @@
-// Flexible right-preconditioned restarted GMRES (FGMRES) with device-resident Hessenberg/Givens state.
+// Flexible right-preconditioned restarted GMRES (FGMRES) and BiCGStab.  Vectors, the Gram-Schmidt passes and
+// their reductions live on the device; the (m+1) x m Hessenberg / Givens algebra and the convergence decision
+// run on the host from one small read per iteration (written by a kernel into page-locked host memory).
 // Replaces PETSc KSP(preonly)+PC(lu) behind DOLFINx NewtonSolver (reference solvers.py:52,179).
 #pragma once
 #include <functional>
