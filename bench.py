@@ -414,8 +414,10 @@ def main():
         traffic = None
         tf = ROOT / "profiles" / "r2_traffic.json"
         if tf.exists() and world == 1 and not weak:
-            t_ = json.loads(tf.read_text()).get("amg_cheby_fine", {})
-            if t_.get("nside") == nside:
+            t_all = json.loads(tf.read_text())
+            t_ = t_all.get("amg_cheby_fine_fp32") or t_all.get("amg_cheby_fine", {})
+            # the capture is of the fp32 level copy: not valid for the opt-in half-precision smoother
+            if t_.get("nside") == nside and levels and levels[0]["value_bytes"] == 4:
                 traffic = t_["traffic_bytes"]       # dram read+write per launch, ncu --set full (profiles/)
         if levels:
             l0 = levels[0]

@@ -108,6 +108,12 @@ typedef struct shakti_options {
                                    above 1e-2 ||F_k||); 0 = always solve to linear_rtol ||F_0|| (closest to the reference's LU) */
   int32_t amg_replicate_below;  /* multi-GPU: the first AMG level with at most this many rows in total, and every level below
                                    it, is replicated on all ranks and solved without communication (default 100000) */
+  double newton_relaxation;     /* DOLFINx NewtonSolver.relaxation_parameter: x <- x - relaxation * dx.  Default 1, which is what
+                                   the reference runs with (solvers.py:52 leaves the attribute alone) */
+  int32_t newton_line_search;   /* 0 (default) = the reference's plain Newton step.  k > 0 = backtracking line search on
+                                   ||F||_2: the step length starts at newton_relaxation and is halved, at most k times, until
+                                   ||F(x - s dx)|| <= (1 - 1e-4 s) ||F(x)|| (an extension named by BASELINE.json's north_star;
+                                   DOLFINx has none).  A step that is accepted at full length costs nothing extra. */
 } shakti_options;
 
 typedef struct shakti_stats {
@@ -119,6 +125,7 @@ typedef struct shakti_stats {
   double amg_operator_complexity;
   double last_residual, last_residual0;  /* Newton: ||F|| at exit and the r0 used               */
   double last_linear_relres;
+  int64_t newton_backtracks;             /* step halvings taken by the line search (newton_line_search > 0) */
 } shakti_stats;
 
 /* ---------------------------------------------------------------- lifetime */

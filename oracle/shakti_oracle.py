@@ -104,6 +104,8 @@ class ShaktiOracle:
         self.rtol, self.atol, self.max_it = 1e-9, 1e-10, 50
         self.newton_r0 = newton_r0
         self._residual0 = 0.0
+        self.relaxation = 1.0                     # NewtonSolver.relaxation_parameter default
+        self.line_search, self.backtracks = 0, 0  # extension (off = reference behaviour), see newton()
         self.rowptr, self.col = csr_pattern(nv, self.cells)
         self._geometry()
         self._slots()
@@ -277,16 +279,29 @@ class ShaktiOracle:
         conv = check(r)
         it = 0
         self.residual_history = [r]
+        self.step_lengths = []
         while not conv and it < self.max_it:
             F, vals = self.assemble(dt)
             J = self.jacobian_matrix(vals).tocsc()
             dx = spla.splu(J).solve(F)
-            self.N = self.N - dx
+            lam = self.relaxation                     # NewtonSolver.relaxation_parameter (1 in the reference)
+            self.N = self.N - lam * dx
             it += 1
             F, _ = self.assemble(dt, want_J=False)
             if it == 1 and self.newton_r0 == "dolfinx":
                 self._residual0 = np.linalg.norm(dx)
-            r = np.linalg.norm(F)
+            r_old, r = r, np.linalg.norm(F)
+            # backtracking line search -- NOT in the reference (DOLFINx has none); restated here only as the
+            # checker of the library's opt-in newton_line_search (same rule, same update order)
+            nb = 0
+            while nb < self.line_search and not (r <= (1.0 - 1e-4 * lam) * r_old):
+                self.N = self.N + 0.5 * lam * dx
+                lam *= 0.5
+                nb += 1
+                F, _ = self.assemble(dt, want_J=False)
+                r = np.linalg.norm(F)
+            self.backtracks += nb
+            self.step_lengths.append(lam)
             self.residual_history.append(r)
             conv = check(r)
         if not conv:

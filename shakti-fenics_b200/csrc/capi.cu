@@ -355,7 +355,11 @@ static void newton_solve(shakti_model* m, double dt, int32_t* niter, int32_t* co
   double r_prev = -1.0;
   // With the DOLFINx r0 the Newton test is loose and scale dependent (the iteration often stops long
   // before it has converged), so the iterate it stops at depends on every solve: no forcing there.
-  const double forcing = m->opt.newton_r0 == SHAKTI_R0_DOLFINX ? 0.0 : m->opt.linear_forcing;
+  // Likewise with an under-relaxed step the iteration converges linearly and the quadratic model behind
+  // the forcing terms does not hold.
+  const double relax = m->opt.newton_relaxation;
+  SHAKTI_REQUIRE(relax > 0, "newton_relaxation must be positive");
+  const double forcing = (m->opt.newton_r0 == SHAKTI_R0_DOLFINX || relax != 1.0) ? 0.0 : m->opt.linear_forcing;
   const bool hist_ok = m->hist_ratio > 0 && m->hist_dt > 0 && std::fabs(dt / m->hist_dt - 1.0) < 0.5;
   const double tau_tight = m->opt.linear_rtol * r_init;
   double tau_last = tau_tight;
@@ -379,21 +383,37 @@ static void newton_solve(shakti_model* m, double dt, int32_t* niter, int32_t* co
       throw Error(SHAKTI_ERR_LINEAR, "Krylov solve did not reach its tolerance (relres " +
                                          std::to_string(kr.relres) + " after " + std::to_string(kr.iterations) + " its)");
     if (m->n_bc) SHAKTI_LAUNCH(fix_bc_dx_kernel, div_up(no, 256), 256, 0, m->stream, no, m->isbc.p, m->F.p, m->dx.p);
-    launch_axpy(no, -1.0, m->dx.p, m->N.p, m->stream);   // x <- x - dx
+    double lam = relax;
+    launch_axpy(no, -lam, m->dx.p, m->N.p, m->stream);   // x <- x - relaxation dx   (relaxation = 1 in the reference)
     m->halo.exchange(m->N.p, m->stream);
     ++it;
     if (it == 1 && m->opt.newton_r0 == SHAKTI_R0_DOLFINX) m->residual0 = norm2(m, m->dx.p);
     // The Jacobian is only needed if another iteration follows: when the model says this one converged
     // with a decade to spare, assemble the residual alone (and the Jacobian after all if it did not)
     const bool expect_conv = forcing > 0 && pred >= 0 && 10.0 * (pred + tau) < newton_target();
-    assemble(m, dt, expect_conv ? 0 : 1);
+    bool have_J = !expect_conv;
+    assemble(m, dt, have_J ? 1 : 0);
     r_prev = r;
     r = norm2(m, m->F.p);
+    // Backtracking line search (newton_line_search > 0; not in the reference): halve the step until the
+    // residual norm has decreased sufficiently.  N currently holds x - lam dx; x - lam/2 dx = N + lam/2 dx.
+    // A NaN residual (state outside the model's range) fails the test and is backtracked like an increase.
+    int nb = 0;
+    while (nb < m->opt.newton_line_search && !(r <= (1.0 - 1e-4 * lam) * r_prev)) {
+      launch_axpy(no, 0.5 * lam, m->dx.p, m->N.p, m->stream);
+      m->halo.exchange(m->N.p, m->stream);
+      lam *= 0.5;
+      ++nb;
+      assemble(m, dt, 0);
+      have_J = false;
+      r = norm2(m, m->F.p);
+    }
+    m->st.newton_backtracks += nb;
     conv = check(r);
-    if (!conv && expect_conv) assemble(m, dt, 1);
+    if (!conv && !have_J) assemble(m, dt, 1);
     if (trace && comm().rank == 0)
-      fprintf(stderr, "[newton]   it %d krylov %d (rtol %.2e) r %.6e rel %.3e%s\n", it, kr.iterations, rtol_k, r, rel_of(r),
-              expect_conv ? " F-only" : "");
+      fprintf(stderr, "[newton]   it %d krylov %d (rtol %.2e) r %.6e rel %.3e step %.4g%s\n", it, kr.iterations, rtol_k, r,
+              rel_of(r), lam, expect_conv ? " F-only" : "");
     if (it == 1) { m->hist_ratio = r_prev > 0 ? r / r_prev : -1.0; m->hist_dt = dt; }
     if (conv && tau_last > tau_tight) {
       // The iteration converged one step earlier than the model expected, i.e. after a LOOSE solve.  The
@@ -760,6 +780,8 @@ int shakti_default_options(shakti_options* o) {
   o->b_min = 1.0e-5; o->assembly_kernel = 0; o->reorder = 1;
   o->linear_forcing = 0.01;
   o->amg_replicate_below = 100000;
+  o->newton_relaxation = 1.0;
+  o->newton_line_search = 0;
   return SHAKTI_OK;
 }
 

@@ -51,6 +51,7 @@ class Options(C.Structure):
         ("amg_cuda_graph", C.c_int32), ("amg_smoother_halo", C.c_int32),
         ("b_min", C.c_double), ("assembly_kernel", C.c_int32), ("reorder", C.c_int32),
         ("linear_forcing", C.c_double), ("amg_replicate_below", C.c_int32),
+        ("newton_relaxation", C.c_double), ("newton_line_search", C.c_int32),
     ]
 
 
@@ -58,7 +59,8 @@ class Stats(C.Structure):
     _fields_ = [(k, C.c_int64) for k in (
         "n_vert", "n_cell", "nnz", "n_owned", "n_local", "n_cell_local", "nnz_local", "steps", "newton_its",
         "linear_its", "kernel_launches", "amg_levels", "amg_refreshes")] + [
-        (k, C.c_double) for k in ("amg_operator_complexity", "last_residual", "last_residual0", "last_linear_relres")]
+        (k, C.c_double) for k in ("amg_operator_complexity", "last_residual", "last_residual0", "last_linear_relres")] + [
+        ("newton_backtracks", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -107,8 +107,10 @@ class B200NewtonSolver:
 
     def _push_newton_options(self):
         o = self.model.options
-        if (o.newton_rtol, o.newton_atol, o.newton_max_it) != (self.rtol, self.atol, self.max_it):
-            self.model.set_options(newton_rtol=self.rtol, newton_atol=self.atol, newton_max_it=self.max_it)
+        want = (self.rtol, self.atol, self.max_it, float(self.relaxation_parameter))
+        if (o.newton_rtol, o.newton_atol, o.newton_max_it, o.newton_relaxation) != want:
+            self.model.set_options(newton_rtol=self.rtol, newton_atol=self.atol, newton_max_it=self.max_it,
+                                   newton_relaxation=float(self.relaxation_parameter))
 
     def solve(self, N):
         """niter, converged = solver.solve(N)   (reference solvers.py:179).  Raises RuntimeError

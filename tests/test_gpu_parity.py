@@ -432,3 +432,28 @@ def test_device_data_ingestion_matches_scipy_and_numpy():
         assert np.array_equal(m.get_field("storage") != 0, points_in_polygon(xy[:, 0], xy[:, 1], poly))
     finally:
         m.close()
+
+
+@pytest.mark.parametrize("relaxation, line_search", [(0.7, 0), (2.5, 3), (1.0, 4)],
+                         ids=["under-relaxed", "overshoot+backtracking", "line-search-idle"])
+def test_newton_relaxation_and_line_search(relaxation, line_search):
+    """NewtonSolver.relaxation_parameter (x <- x - relaxation dx, DOLFINx; 1 in the reference) and the
+    opt-in backtracking line search: iteration counts, accepted step lengths (through the number of
+    halvings) and the converged field equal the oracle's.  relaxation = 2.5 overshoots, so every step is
+    halved once to 1.25; with relaxation = 1 the search never acts and the result is the plain iteration's."""
+    c = make_case(seed=1)
+    o = make_oracle(*c)
+    o.relaxation, o.line_search = relaxation, line_search
+    m = make_model(*c, newton_relaxation=relaxation, newton_line_search=line_search)
+    try:
+        it_o, _ = o.newton(DT)
+        it_m, conv = m.newton_solve(DT)
+        assert conv and it_m == it_o
+        assert m.stats()["newton_backtracks"] == o.backtracks
+        if relaxation == 2.5:
+            assert o.backtracks == it_o and set(o.step_lengths) == {1.25}
+        if relaxation == 1.0:
+            assert o.backtracks == 0
+        assert relinf(m.get_field("N"), o.N) < 1e-8
+    finally:
+        m.close()

@@ -29,6 +29,18 @@ def test_struct_layouts_match_header():
     o = capi.default_options()
     assert (o.newton_rtol, o.newton_atol, o.newton_max_it) == (1e-9, 1e-10, 50)
     assert o.b_min == 1e-5 and o.reorder == 1 and o.gmres_restart > 0
+    # the LAST members: any disagreement about the layout in between would show here
+    assert o.linear_forcing == 0.01 and o.amg_replicate_below == 100000
+    assert o.newton_relaxation == 1.0 and o.newton_line_search == 0      # the reference's plain Newton step
+    hdr = (ROOT / "include" / "shakti_b200.h").read_text()
+    body = hdr[hdr.index("typedef struct shakti_options {"):hdr.index("} shakti_options;")]
+    names = re.findall(r"\b(?:double|int32_t)\s+([^;]+);", body)
+    names = [n.strip() for grp in names for n in grp.split(",")]
+    assert names == [f for f, _ in capi.Options._fields_]
+    body = hdr[hdr.index("typedef struct shakti_stats {"):hdr.index("} shakti_stats;")]
+    names = re.findall(r"\b(?:double|int64_t)\s+([^;]+);", body)
+    names = [n.strip() for grp in names for n in grp.split(",")]
+    assert names == [f for f, _ in capi.Stats._fields_]
     p = capi.default_params()
     import sys
     sys.path.insert(0, str(ROOT / "shakti-fenics_b200" / "source"))

@@ -182,3 +182,28 @@ def test_csr_pattern_and_dirichlet_dofs_small():
     assert col.tolist() == [0, 1, 2, 3, 0, 1, 2, 0, 1, 2, 3, 0, 2, 3]
     d = dirichlet_dofs(xy, cells, lambda x: np.isclose(x[0], 0.0))
     assert d.tolist() == [0, 3]
+
+
+def test_newton_relaxation_and_line_search_restatement():
+    """The oracle's relaxation parameter (DOLFINx NewtonSolver.relaxation_parameter) and the backtracking rule the
+    library's opt-in newton_line_search is checked against: defaults reproduce the plain iteration exactly; an
+    overshooting step (2.5 dx) is halved once per iteration; every accepted step satisfies the decrease test."""
+    c = make_case(seed=1)
+    o0 = make_oracle(*c)
+    it0, _ = o0.newton(3600.0)
+    o1 = make_oracle(*c)
+    o1.line_search = 4
+    it1, _ = o1.newton(3600.0)
+    assert it1 == it0 and o1.backtracks == 0 and np.array_equal(o1.N, o0.N)
+    o2 = make_oracle(*c)
+    o2.relaxation, o2.line_search = 2.5, 3
+    it2, conv = o2.newton(3600.0)
+    assert conv and o2.backtracks == it2 and set(o2.step_lengths) == {1.25}
+    r = np.array(o2.residual_history)
+    assert np.all(r[1:] <= (1 - 1e-4 * 1.25) * r[:-1])
+    # same root whatever the path (a linearly convergent iteration stops ~1e-7 away from it at rtol 1e-9)
+    assert relinf(o2.N, o0.N) < 1e-6
+    o3 = make_oracle(*c)
+    o3.relaxation = 0.7
+    it3, _ = o3.newton(3600.0)
+    assert it3 > it0 and relinf(o3.N, o0.N) < 1e-6
