@@ -110,9 +110,20 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------ CPU arm
+def _oracle_backend():
+    """The CPU arm runs the oracle's compiled element kernels (oracle/shakti_oracle_c.c, OpenMP over cells -- the
+    reference's element kernels are FFCx-generated C as well) when `make -C oracle` has built them, with the
+    fill-reducing MMD(A'+A) ordering for SuperLU; otherwise the numpy restatement.  Both are the same algorithm
+    (tests/test_oracle.py: 1e-13)."""
+    from oracle import cbackend
+    if cbackend.available():
+        return dict(backend="c", permc_spec="MMD_AT_PLUS_A"), cbackend.threads(), "C element kernels (OpenMP) + scipy SuperLU, MMD(A'+A) ordering"
+    return {}, cpu_threads(), "numpy element kernels + scipy SuperLU"
+
+
 def _oracle_for(case):
     from oracle.shakti_oracle import ShaktiOracle
-    o = ShaktiOracle(case.xy, case.cells)
+    o = ShaktiOracle(case.xy, case.cells, **_oracle_backend()[0])
     for k in ("z_b", "z_s", "G", "inputs", "storage", "b", "N_n", "melt_n"):
         getattr(o, k)[:] = case.fields[k]
     o.q[:] = case.fields["q"]
@@ -156,7 +167,8 @@ def cpu_oracle_rate(nside, steps, warmup, target_dofs):
     el, cpu = time.perf_counter() - t0, time.process_time() - c0
     raw = steps / el
     scaled = raw * (case.n_vert / float(target_dofs))
-    sample = (f"{steps} oracle steps (numpy assembly + scipy SuperLU; BLAS pool of {cpu_threads()} threads, measured CPU time / wall "
+    _, thr, what = _oracle_backend()
+    sample = (f"{steps} oracle steps ({what}; {thr} threads for the element loops, the sparse LU itself is serial; measured CPU time / wall "
               f"time = {cpu / el:.1f} cores busy) on a {nside}x{nside}-vertex C4 mesh "
               f"({case.n_vert} dofs, {np.mean(its):.1f} Newton its/step): {raw:.4g} steps/s measured; `value` is that rate "
               f"EXTRAPOLATED by the dofs ratio {case.n_vert}/{target_dofs} (linear, optimistic for LU)")
@@ -186,7 +198,8 @@ def same_config_c2(cpu_steps=2, gpu_steps=20):
     its = [o.step(dt)[0] for dt in dts[2:2 + cpu_steps]]
     out["cpu_steps_s"] = cpu_steps / (time.perf_counter() - t0)
     out["cpu_steps"] = cpu_steps
-    out["cpu_threads"] = cpu_threads()
+    out["cpu_threads"] = _oracle_backend()[1]
+    out["cpu_impl"] = _oracle_backend()[2]
     out["cpu_newton_its"] = [int(i) for i in its]
     its_g = m.run(dts[2:2 + cpu_steps])
     out["gpu_newton_its"] = [int(i) for i in its_g]
@@ -212,7 +225,7 @@ def run_reference(args):
     target = nside * nside
     nside_cpu = cpu_sample_nside(args.cpu_sample_nside, args.steps + 1)
     scaled, raw, sample, el = cpu_oracle_rate(nside_cpu, args.steps, min(args.warmup, 1), target)
-    threads = cpu_threads()
+    threads = _oracle_backend()[1]
     line = {
         "impl": "reference", "metric": METRIC, "value": scaled, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": min(args.warmup, 1), "ms_per_step": 1e3 / scaled, "higher_is_better": True, "scaling": "strong",
@@ -444,7 +457,7 @@ def main():
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1 and not weak:
         scaled, raw, sample, _ = cpu_oracle_rate(cpu_sample_nside(args.cpu_sample_nside, 5), 2, 1, nv)
-        cpu_baseline = {"value": scaled, "unit": UNIT, "cores": cpu_threads(), "kind": "port", "sample": sample,
+        cpu_baseline = {"value": scaled, "unit": UNIT, "cores": _oracle_backend()[1], "kind": "port", "sample": sample,
                         "raw_steps_per_sec_on_sample": raw, "extrapolated": True,
                         "same_config": same_config_c2()}
     n_newton = st1["newton_its"] - st0["newton_its"]

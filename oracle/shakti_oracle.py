@@ -84,7 +84,16 @@ def dirichlet_dofs(xy, cells, marker):
 
 
 class ShaktiOracle:
-    def __init__(self, xy, cells, params=None, quad=None, newton_r0="initial_residual"):
+    def __init__(self, xy, cells, params=None, quad=None, newton_r0="initial_residual", backend="numpy",
+                 permc_spec="COLAMD"):
+        """backend: "numpy" (the restatement every parity test uses) or "c" (oracle/shakti_oracle_c.c: the same
+        per-quadrature-point formulas compiled, OpenMP over cells -- what bench.py times as the CPU baseline, since
+        the reference's element kernels are compiled C too).  permc_spec: SuperLU column ordering of the LU solve
+        ("MMD_AT_PLUS_A" halves the fill on these symmetric-pattern matrices; the reference's PETSc LU packages
+        order with nested dissection / AMD as well)."""
+        if backend not in ("numpy", "c"):
+            raise ValueError(backend)
+        self.backend, self.permc_spec = backend, permc_spec
         self.xy = np.ascontiguousarray(xy, dtype=np.float64)
         self.cells = np.ascontiguousarray(cells, dtype=np.int32)
         self.nv = self.xy.shape[0]
@@ -168,6 +177,9 @@ class ShaktiOracle:
     def kbar(self):
         """|detJ| sum_k w_k K(b(xi_k), |q(xi_k)|)   (constitutive.py:11-20)."""
         p = self.p
+        if self.backend == "c":
+            from . import cbackend
+            return cbackend.kbar(self)
         bc = self.b[self.cells]
         qc = self.q[self.cells]
         out = np.zeros(self.ne)
@@ -184,6 +196,9 @@ class ShaktiOracle:
         """Element residual (ne,3) and Jacobian (ne,3,3), every term at every quadrature point."""
         p = self.p
         N = self.N if N is None else N
+        if self.backend == "c":
+            from . import cbackend
+            return cbackend.element_FJ(self, dt, N, want_J)
         c = self.cells
         gp = self.gradphi
         h = self.head(N)
@@ -283,7 +298,7 @@ class ShaktiOracle:
         while not conv and it < self.max_it:
             F, vals = self.assemble(dt)
             J = self.jacobian_matrix(vals).tocsc()
-            dx = spla.splu(J).solve(F)
+            dx = spla.splu(J, permc_spec=self.permc_spec).solve(F)
             lam = self.relaxation                     # NewtonSolver.relaxation_parameter (1 in the reference)
             self.N = self.N - lam * dx
             it += 1
@@ -359,9 +374,13 @@ class ShaktiOracle:
     def step(self, dt):
         """One pass of solvers.py:179-229 (without output)."""
         it, conv = self.newton(dt)
-        self.update_q()
-        self.update_melt()
-        self.update_b(dt)
+        if self.backend == "c":
+            from . import cbackend
+            self.q, self.melt_n, self.b = cbackend.nodal_updates(self, dt)
+        else:
+            self.update_q()
+            self.update_melt()
+            self.update_b(dt)
         self.N_n = self.N.copy()
         return it, conv
 
