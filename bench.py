@@ -142,13 +142,22 @@ def cpu_threads():
     return int(n)
 
 
-def cpu_sample_nside(requested, steps):
-    """Bounded CPU sample: 70-200 us of oracle time per dof and step (measured on the host cores of
-    the GPU box and of the build container), sized for one to two minutes in total."""
+def cpu_sample_nside(requested, n_steps, budget_s=90.0):
+    """Bounded CPU sample: the mesh side whose `n_steps` oracle steps (the first one from the initial state:
+    ~10 Newton iterations instead of 3) take about `budget_s` seconds.  Cost model measured with the compiled
+    element kernels + SuperLU/MMD on the build container's cores: (30 + 0.07 sqrt(dofs)) us per dof and step
+    (39 us at 40k dofs, 72 us at 490k, 101 us at 1M: the sparse LU is super-linear)."""
     if requested:
         return requested
-    dofs = 90.0 / (max(steps, 1) * 1.2e-4)
-    return int(min(500, max(100, dofs ** 0.5)))
+    per_step = budget_s / (max(n_steps, 1) - 1 + 3.3)
+    lo, hi = 1.0e4, 1.0e6
+    for _ in range(40):
+        d = 0.5 * (lo + hi)
+        if d * 1e-6 * (30.0 + 0.07 * d ** 0.5) > per_step:
+            hi = d
+        else:
+            lo = d
+    return int(min(1000, max(100, lo ** 0.5)))
 
 
 def cpu_oracle_rate(nside, steps, warmup, target_dofs):
@@ -456,7 +465,7 @@ def main():
     m.close()
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1 and not weak:
-        scaled, raw, sample, _ = cpu_oracle_rate(cpu_sample_nside(args.cpu_sample_nside, 5), 2, 1, nv)
+        scaled, raw, sample, _ = cpu_oracle_rate(cpu_sample_nside(args.cpu_sample_nside, 3), 2, 1, nv)
         cpu_baseline = {"value": scaled, "unit": UNIT, "cores": _oracle_backend()[1], "kind": "port", "sample": sample,
                         "raw_steps_per_sec_on_sample": raw, "extrapolated": True,
                         "same_config": same_config_c2()}

@@ -10,4 +10,8 @@ vectors.  This oracle is a restatement of ``source/solvers.py``
 ``source/constitutive.py`` with the documented third-party semantics; it is pinned only by
 independent mathematics (exact symbolic integrals, finite-difference Jacobians, patch tests,
 manufactured fixtures under ``tests/golden/``).
+
+Files: ``shakti_oracle.py`` (numpy; the checker of the parity tests), ``shakti_oracle_c.c`` + ``cbackend.py``
+(the same element formulas compiled with OpenMP, ``make -C oracle``; what bench.py times as the CPU baseline),
+``quadrature.py`` (rule tables + validator).
 """

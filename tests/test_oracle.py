@@ -207,3 +207,40 @@ def test_newton_relaxation_and_line_search_restatement():
     o3.relaxation = 0.7
     it3, _ = o3.newton(3600.0)
     assert it3 > it0 and relinf(o3.N, o0.N) < 1e-6
+
+
+@pytest.fixture(scope="module")
+def c_backend():
+    """oracle/shakti_oracle_c.c, built on demand (gcc is part of the image; __graft_entry__.build() does the same)."""
+    import subprocess
+    from oracle import cbackend
+    subprocess.run(["make", "-C", str(Path(__file__).resolve().parent.parent / "oracle")], check=True, capture_output=True)
+    assert cbackend.available() and cbackend.threads() >= 1
+    return cbackend
+
+
+@pytest.mark.parametrize("kw", [dict(seed=3), dict(seed=4, neg_b=True, turbulent=False), dict(seed=5, storage=False)],
+                         ids=["rough-fields", "negative-gap", "no-storage"])
+def test_c_backend_is_the_same_restatement(c_backend, kw):
+    """The compiled element kernels (the CPU baseline bench.py times) against the numpy oracle: element residual and
+    Jacobian, Kbar and three full time steps incl. the last-cell-wins nodal updates and the clamp."""
+    c = make_case(nx=30, ny=20, **kw)
+    o1, o2 = make_oracle(*c), make_oracle(*c, backend="c")
+    for dt in (3600.0, 360.0):
+        (F1, J1), (F2, J2) = o1.element_FJ(dt), o2.element_FJ(dt)
+        assert relinf(F2, F1) < 1e-13 and relinf(J2, J1) < 1e-13
+        assert o2.element_FJ(dt, want_J=False)[1] is None
+    assert relinf(o2.kbar(), o1.kbar()) < 1e-13
+    # the three nodal updates from an identical state (N moved away from N_n so that every term is active)
+    o1, o2 = make_oracle(*c), make_oracle(*c, backend="c")
+    o1.N[:] = o2.N[:] = c[2]["N_n"] * 1.01
+    o1.update_q(); o1.update_melt(); o1.update_b(3600.0)
+    q, melt, b = c_backend.nodal_updates(o2, 3600.0)
+    assert relinf(q, o1.q) < 1e-13 and relinf(melt, o1.melt_n) < 1e-12 and relinf(b, o1.b) < 1e-13
+    assert (b == o1.b_min).sum() == (o1.b == o1.b_min).sum()
+    if kw.get("neg_b"):
+        return                               # the first Newton solve of this state is chaotic (LU-conditioning bound)
+    o1, o2 = make_oracle(*c), make_oracle(*c, backend="c", permc_spec="MMD_AT_PLUS_A")
+    for dt in (360.0, 3600.0, 3600.0):
+        assert o1.step(dt)[0] == o2.step(dt)[0]
+    assert relinf(o2.N, o1.N) < 1e-10 and relinf(o2.b, o1.b) < 1e-10 and relinf(o2.melt_n, o1.melt_n) < 1e-9
