@@ -21,12 +21,13 @@ def rectangle(nx, ny, lx, ly, x0=0.0, y0=0.0, jitter=0.0, seed=1234, diagonal="r
     rng = np.random.default_rng(seed)
     if jitter > 0.0:
         hx, hy = lx / nx, ly / ny
-        interior = np.zeros((ny + 1, nx + 1), dtype=bool)
-        interior[1:-1, 1:-1] = True
-        m = interior.ravel()
-        d = rng.uniform(-jitter, jitter, size=(int(m.sum()), 2))
-        xy[m, 0] += d[:, 0] * hx
-        xy[m, 1] += d[:, 1] * hy
+        # one (dx, dy) pair per interior vertex, drawn in vertex order (row-major over the interior block)
+        d = rng.uniform(-jitter, jitter, size=(max(ny - 1, 0) * max(nx - 1, 0), 2))
+        if d.size:
+            d = d.reshape(ny - 1, nx - 1, 2)
+            g = xy.reshape(ny + 1, nx + 1, 2)
+            g[1:-1, 1:-1, 0] += d[:, :, 0] * hx
+            g[1:-1, 1:-1, 1] += d[:, :, 1] * hy
     ix, iy = np.meshgrid(np.arange(nx), np.arange(ny))
     v00 = (iy * (nx + 1) + ix).ravel()
     v10 = v00 + 1
@@ -43,11 +44,15 @@ def rectangle(nx, ny, lx, ly, x0=0.0, y0=0.0, jitter=0.0, seed=1234, diagonal="r
     else:
         raise ValueError(f"unknown diagonal {diagonal!r}")
     # right: (v00,v10,v11),(v00,v11,v01); left: (v00,v10,v01),(v10,v11,v01)
-    t0 = np.where(flip[:, None], np.stack([v00, v10, v01], 1), np.stack([v00, v10, v11], 1))
-    t1 = np.where(flip[:, None], np.stack([v10, v11, v01], 1), np.stack([v00, v11, v01], 1))
     cells = np.empty((2 * v00.size, 3), dtype=np.int32)
-    cells[0::2] = t0
-    cells[1::2] = t1
+    if not flip.any():                                # written column by column: no (n,3) int64 temporaries
+        cols0, cols1 = (v00, v10, v11), (v00, v11, v01)
+    else:
+        cols0 = (v00, v10, np.where(flip, v01, v11))
+        cols1 = (np.where(flip, v10, v00), v11, v01)
+    for k in range(3):
+        cells[0::2, k] = cols0[k]
+        cells[1::2, k] = cols1[k]
     return xy, cells
 
 
