@@ -5,11 +5,26 @@
 #include <cmath>
 #include <cstdlib>
 #include <functional>
+#include <memory>
 #include <numeric>
 #include <stdexcept>
 #include <thread>
 
+#include <chrono>
+#include <cstdio>
+
 namespace shakti {
+
+// SHAKTI_TRACE_PREP=1: wall time of every preprocessing phase on stderr (lap("name") closes a phase)
+struct PrepLaps {
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  void operator()(const char* name) {
+    static const bool on = getenv("SHAKTI_TRACE_PREP") != nullptr;
+    const auto now = std::chrono::steady_clock::now();
+    if (on) fprintf(stderr, "[prep] %-32s %8.3f s\n", name, std::chrono::duration<double>(now - t).count());
+    t = now;
+  }
+};
 
 // ------------------------------------------------------------------ host threads
 // The preprocessing is embarrassingly parallel over rows / cells / blocks; it runs once per model but on
@@ -123,81 +138,87 @@ HostCsr csr_transpose(const HostCsr& a, std::vector<int32_t>* entry_map) {
 
 // adjacency (incl. diagonal) of rows [0,n_rows) given cells in some numbering; a row is
 // built only if row_of(vertex) >= 0.
+struct RawAdj : HostCsr {
+  std::unique_ptr<int32_t[]> raw;   // unsorted neighbour lists; rowptr indexes it until finish_rows has run
+};
 template <class RowOf>
-static HostCsr adjacency(int64_t n_rows, int64_t n_cols, int64_t ne, const int32_t* cells, RowOf row_of) {
-  HostCsr a;
+static RawAdj adjacency(int64_t n_rows, int64_t n_cols, int64_t ne, const int32_t* cells, RowOf row_of) {
+  // Unsorted neighbour lists (with duplicates) of rows [0, n_rows): every cell contributes the two other
+  // vertices to each of its rows, plus one trailing placeholder per row for the diagonal.  Counting and
+  // filling run on all host threads with relaxed atomic counters; the order inside a row is therefore
+  // arbitrary, which does not matter because finish_rows sorts every row.
+  RawAdj a;
   a.n_rows = n_rows;
   a.n_cols = n_cols;
+  PrepLaps lap;
   std::vector<int32_t> cnt(n_rows + 1, 0);
-  for (int64_t e = 0; e < ne; ++e)
-    for (int i = 0; i < 3; ++i) {
-      int64_t r = row_of(cells[3 * e + i]);
-      if (r >= 0) cnt[r + 1] += 2;
-    }
-  for (int64_t r = 0; r < n_rows; ++r) cnt[r + 1] += 1;  // diagonal
+  parallel_for(ne, [&](int64_t e0, int64_t e1, int) {
+    for (int64_t e = e0; e < e1; ++e)
+      for (int i = 0; i < 3; ++i) {
+        const int64_t r = row_of(cells[3 * e + i]);
+        if (r >= 0) __atomic_fetch_add(&cnt[r + 1], 2, __ATOMIC_RELAXED);
+      }
+  });
+  lap("  adjacency: count");
   std::vector<int64_t> ptr(n_rows + 1, 0);
-  for (int64_t r = 0; r < n_rows; ++r) ptr[r + 1] = ptr[r] + cnt[r + 1];
-  std::vector<int32_t> tmp(ptr[n_rows]);
+  for (int64_t r = 0; r < n_rows; ++r) ptr[r + 1] = ptr[r] + cnt[r + 1] + 1;  // + the diagonal
+  if (ptr[n_rows] > 2000000000LL) throw std::runtime_error("adjacency too large for int32 offsets");
+  // not value-initialised: zero-filling 0.8 GB on one thread (16M dofs) cost more than counting and filling;
+  // every element is written below, the pages are first touched by the threads that fill them
+  std::unique_ptr<int32_t[]> tmp_own(new int32_t[(size_t)ptr[n_rows]]);
+  int32_t* tmp = tmp_own.get();
   std::vector<int64_t> fill(ptr.begin(), ptr.end() - 1);
-  for (int64_t e = 0; e < ne; ++e)
-    for (int i = 0; i < 3; ++i) {
-      int32_t v = cells[3 * e + i];
-      int64_t r = row_of(v);
-      if (r < 0) continue;
-      tmp[fill[r]++] = cells[3 * e + (i + 1) % 3];
-      tmp[fill[r]++] = cells[3 * e + (i + 2) % 3];
-    }
-  a.rowptr.assign(n_rows + 1, 0);
-  // first pass: sort/unique in place, record lengths
-  std::vector<int32_t> len(n_rows);
-  for (int64_t r = 0; r < n_rows; ++r) {
-    int32_t* b = tmp.data() + ptr[r];
-    int32_t* e = tmp.data() + fill[r];
-    *e++ = -1;  // placeholder for the diagonal, patched by the caller via diag_of
-    len[r] = (int32_t)(e - b);
-  }
-  // the diagonal column id equals the vertex id whose row this is; recover it from cells
-  // by letting the caller supply it: rows are indexed so that row r <-> some vertex id.
-  // To stay generic we rebuild: mark diag after we know it (see wrappers below).
-  a.col.swap(tmp);
+  lap("  adjacency: alloc");
+  parallel_for(ne, [&](int64_t e0, int64_t e1, int) {
+    for (int64_t e = e0; e < e1; ++e)
+      for (int i = 0; i < 3; ++i) {
+        const int64_t r = row_of(cells[3 * e + i]);
+        if (r < 0) continue;
+        const int64_t p = __atomic_fetch_add(&fill[r], (int64_t)2, __ATOMIC_RELAXED);
+        tmp[p] = cells[3 * e + (i + 1) % 3];
+        tmp[p + 1] = cells[3 * e + (i + 2) % 3];
+      }
+  });
+  lap("  adjacency: fill");
+  // (the last slot of every row is the diagonal's: finish_rows writes its id there)
+  a.raw = std::move(tmp_own);
   a.rowptr.resize(n_rows + 1);
-  // stash ptr/len in rowptr temporarily (64-bit safe for our sizes < 2^31)
   for (int64_t r = 0; r <= n_rows; ++r) a.rowptr[r] = (int32_t)ptr[r];
-  (void)len;
   return a;
 }
 
 // finish: replace the trailing -1 of each row by diag id, sort, unique, compact
-static void finish_rows(HostCsr& a, const std::vector<int32_t>& diag_id) {
-  int64_t n = a.n_rows;
+static void finish_rows(RawAdj& a, const std::vector<int32_t>& diag_id) {
+  const int64_t n = a.n_rows;
+  PrepLaps lap;
   std::vector<int32_t> newptr(n + 1, 0), len(n, 0);
   parallel_for(n, [&](int64_t r0, int64_t r1, int) {
     for (int64_t r = r0; r < r1; ++r) {
-      int32_t* b = a.col.data() + a.rowptr[r];
-      int32_t* e = a.col.data() + a.rowptr[r + 1];
+      int32_t* b = a.raw.get() + a.rowptr[r];
+      int32_t* e = a.raw.get() + a.rowptr[r + 1];
       *(e - 1) = diag_id[r];
       std::sort(b, e);
       len[r] = (int32_t)(std::unique(b, e) - b);
     }
   });
-  int64_t w = 0;
-  for (int64_t r = 0; r < n; ++r) {
-    const int32_t* b = a.col.data() + a.rowptr[r];
-    newptr[r] = (int32_t)w;
-    for (int32_t k = 0; k < len[r]; ++k) a.col[w++] = b[k];  // w <= position of b, safe in place
-  }
-  newptr[n] = (int32_t)w;
-  a.col.resize(w);
-  a.col.shrink_to_fit();
+  lap("  rows: sort + unique");
+  for (int64_t r = 0; r < n; ++r) newptr[r + 1] = newptr[r] + len[r];
+  std::vector<int32_t> col(newptr[n]);
+  parallel_for(n, [&](int64_t r0, int64_t r1, int) {
+    for (int64_t r = r0; r < r1; ++r) std::copy_n(a.raw.get() + a.rowptr[r], len[r], col.data() + newptr[r]);
+  });
+  a.col.swap(col);
   a.rowptr.swap(newptr);
+  a.raw.reset();
+  lap("  rows: compact");
 }
 
 HostCsr caller_csr(int64_t nv, int64_t ne, const int32_t* cells) {
-  HostCsr a = adjacency(nv, nv, ne, cells, [](int32_t v) { return (int64_t)v; });
+  RawAdj a = adjacency(nv, nv, ne, cells, [](int32_t v) { return (int64_t)v; });
   std::vector<int32_t> diag(nv);
   std::iota(diag.begin(), diag.end(), 0);
   finish_rows(a, diag);
-  return a;
+  return HostCsr(std::move(static_cast<HostCsr&>(a)));
 }
 
 std::vector<int32_t> locate_dirichlet_dofs(int64_t nv, int64_t ne, const int32_t* cells,
@@ -233,22 +254,32 @@ std::vector<int32_t> locate_dirichlet_dofs(int64_t nv, int64_t ne, const int32_t
 
 void build_assembly_blocks(const HostMesh& m, int32_t max_cells_per_block, AssemblyBlocks& out) {
   const int32_t no = m.n_owned, ne = m.ne;
+  PrepLaps lap;
   // vertex -> (cell, local index) incidence of owned rows, cells ascending
+  // (counted and filled on all threads with relaxed atomic counters, then every row's short list is sorted:
+  // the same arrays as a serial pass over the cells in ascending order)
   std::vector<int32_t> vptr(no + 1, 0);
-  for (int32_t e = 0; e < ne; ++e)
-    for (int a = 0; a < 3; ++a) {
-      const int32_t r = m.cells[3 * (size_t)e + a];
-      if (r < no) vptr[r + 1]++;
-    }
+  parallel_for(ne, [&](int64_t e0, int64_t e1, int) {
+    for (int64_t e = e0; e < e1; ++e)
+      for (int a = 0; a < 3; ++a) {
+        const int32_t r = m.cells[3 * (size_t)e + a];
+        if (r < no) __atomic_fetch_add(&vptr[r + 1], 1, __ATOMIC_RELAXED);
+      }
+  });
   for (int32_t r = 0; r < no; ++r) vptr[r + 1] += vptr[r];
   std::vector<int32_t> vinc(vptr[no]);   // e*4 + a
   {
     std::vector<int32_t> fill(vptr.begin(), vptr.end() - 1);
-    for (int32_t e = 0; e < ne; ++e)
-      for (int a = 0; a < 3; ++a) {
-        const int32_t r = m.cells[3 * (size_t)e + a];
-        if (r < no) vinc[fill[r]++] = e * 4 + a;
-      }
+    parallel_for(ne, [&](int64_t e0, int64_t e1, int) {
+      for (int64_t e = e0; e < e1; ++e)
+        for (int a = 0; a < 3; ++a) {
+          const int32_t r = m.cells[3 * (size_t)e + a];
+          if (r < no) vinc[__atomic_fetch_add(&fill[r], 1, __ATOMIC_RELAXED)] = (int32_t)e * 4 + a;
+        }
+    });
+    parallel_for(no, [&](int64_t r0, int64_t r1, int) {
+      for (int64_t r = r0; r < r1; ++r) std::sort(vinc.begin() + vptr[r], vinc.begin() + vptr[r + 1]);
+    });
   }
   // Blocks are independent: threads take contiguous runs of blocks, collect their variable-length lists
   // locally and the runs are concatenated in block order afterwards (same arrays as a serial pass).
@@ -258,6 +289,7 @@ void build_assembly_blocks(const HostMesh& m, int32_t max_cells_per_block, Assem
     int32_t max_cells = 0, max_verts = 0;
     bool fits = true, manifold = true;
   };
+  lap("assembly plan: incidence");
   for (int32_t rb : {256, 128, 64, 32}) {
     out = AssemblyBlocks();
     out.rows_per_block = rb;
@@ -334,23 +366,46 @@ void build_assembly_blocks(const HostMesh& m, int32_t max_cells_per_block, Assem
     }, 8);
     bool fits = true, manifold = true;
     for (const Part& P : parts) { fits &= P.fits; manifold &= P.manifold; }
+    lap("assembly plan: blocks");
     if (!fits) continue;
-    // concatenate the runs (threads hold ascending, contiguous block ranges)
-    out.blk_eptr.assign(1, 0);
-    out.blk_hptr.assign(1, 0);
-    out.inc_ptr.assign(1, 0);
-    for (const Part& P : parts) {
+    // concatenate the runs (threads hold ascending, contiguous block ranges): offsets first, then every
+    // run is copied to its place by its own thread
+    const size_t np = parts.size();
+    std::vector<size_t> oe(np + 1, 0), oh(np + 1, 0), oi(np + 1, 0), ob(np + 1, 0), orow(np + 1, 0);
+    for (size_t t = 0; t < np; ++t) {
+      const Part& P = parts[t];
       out.max_cells = std::max(out.max_cells, P.max_cells);
       out.max_verts = std::max(out.max_verts, P.max_verts);
-      out.blk_elems.insert(out.blk_elems.end(), P.elems.begin(), P.elems.end());
-      out.blk_lv.insert(out.blk_lv.end(), P.lv.begin(), P.lv.end());
-      out.blk_halo.insert(out.blk_halo.end(), P.halo.begin(), P.halo.end());
-      out.inc_code.insert(out.inc_code.end(), P.inc.begin(), P.inc.end());
-      for (int32_t c : P.ecount) out.blk_eptr.push_back(out.blk_eptr.back() + c);
-      for (int32_t c : P.hcount) out.blk_hptr.push_back(out.blk_hptr.back() + c);
-      for (int32_t c : P.rowinc) out.inc_ptr.push_back(out.inc_ptr.back() + c);
+      oe[t + 1] = oe[t] + P.elems.size();
+      oh[t + 1] = oh[t] + P.halo.size();
+      oi[t + 1] = oi[t] + P.inc.size();
+      ob[t + 1] = ob[t] + P.ecount.size();
+      orow[t + 1] = orow[t] + P.rowinc.size();
     }
+    out.blk_elems.resize(oe[np]);
+    out.blk_lv.resize(3 * oe[np]);
+    out.blk_halo.resize(oh[np]);
+    out.inc_code.resize(oi[np]);
+    out.blk_eptr.assign(ob[np] + 1, 0);
+    out.blk_hptr.assign(ob[np] + 1, 0);
+    out.inc_ptr.assign(orow[np] + 1, 0);
+    parallel_for((int64_t)np, [&](int64_t t0, int64_t t1, int) {
+      for (int64_t t = t0; t < t1; ++t) {
+        const Part& P = parts[t];
+        std::copy(P.elems.begin(), P.elems.end(), out.blk_elems.begin() + oe[t]);
+        std::copy(P.lv.begin(), P.lv.end(), out.blk_lv.begin() + 3 * oe[t]);
+        std::copy(P.halo.begin(), P.halo.end(), out.blk_halo.begin() + oh[t]);
+        std::copy(P.inc.begin(), P.inc.end(), out.inc_code.begin() + oi[t]);
+        int32_t acc = (int32_t)oe[t];
+        for (size_t k = 0; k < P.ecount.size(); ++k) { acc += P.ecount[k]; out.blk_eptr[ob[t] + k + 1] = acc; }
+        acc = (int32_t)oh[t];
+        for (size_t k = 0; k < P.hcount.size(); ++k) { acc += P.hcount[k]; out.blk_hptr[ob[t] + k + 1] = acc; }
+        acc = (int32_t)oi[t];
+        for (size_t k = 0; k < P.rowinc.size(); ++k) { acc += P.rowinc[k]; out.inc_ptr[orow[t] + k + 1] = acc; }
+      }
+    }, 1);
     out.ok = manifold;
+    lap("assembly plan: concatenate");
     return;
   }
   out.ok = false;
@@ -403,11 +458,13 @@ void build_host_mesh(int64_t nv, int64_t ne, const double* xy, const int32_t* ce
     if (cells[i] < 0 || cells[i] >= nv) throw std::runtime_error("cell vertex id out of range");
   m.nv_g = nv; m.ne_g = ne; m.rank = rank; m.nranks = nranks;
   g_host_thread_share = std::max(1, nranks);
+  PrepLaps lap;
   std::vector<int32_t> order;
   if (reorder) order = morton_order(nv, xy);
   else { order.resize(nv); std::iota(order.begin(), order.end(), 0); }
+  lap("morton order");
   std::vector<int32_t> posof(nv);
-  for (int64_t p = 0; p < nv; ++p) posof[order[p]] = (int32_t)p;
+  parallel_for(nv, [&](int64_t a, int64_t b, int) { for (int64_t p = a; p < b; ++p) posof[order[p]] = (int32_t)p; });
   std::vector<int64_t> bounds(nranks + 1);
   for (int r = 0; r <= nranks; ++r) bounds[r] = (nv * (int64_t)r) / nranks;
   auto owner_of_pos = [&](int64_t p) {
@@ -440,40 +497,50 @@ void build_host_mesh(int64_t nv, int64_t ne, const double* xy, const int32_t* ce
     std::sort(ghost_pos.begin(), ghost_pos.end());
   }
   m.n_local = m.n_owned + (int32_t)ghost_pos.size();
+  lap("local cells + ghosts");
   m.l2g.resize(m.n_local);
-  for (int64_t p = lo; p < hi; ++p) m.l2g[p - lo] = order[p];
+  parallel_for(hi - lo, [&](int64_t a, int64_t b, int) { for (int64_t p = a; p < b; ++p) m.l2g[p] = order[lo + p]; });
   for (size_t k = 0; k < ghost_pos.size(); ++k) m.l2g[m.n_owned + k] = order[ghost_pos[k]];
   m.g2l.assign(nv, -1);
-  for (int32_t l = 0; l < m.n_local; ++l) m.g2l[m.l2g[l]] = l;
+  parallel_for(m.n_local, [&](int64_t a, int64_t b, int) { for (int64_t l = a; l < b; ++l) m.g2l[m.l2g[l]] = (int32_t)l; });
   // cells in local ids, sorted by min local vertex id (stable => ties by caller cell id)
   m.ne = (int32_t)lc.size();
   {
     std::vector<std::pair<int32_t, int32_t>> key(m.ne);
-    for (int32_t k = 0; k < m.ne; ++k) {
-      const int32_t* c = cells + 3 * (int64_t)lc[k];
-      key[k] = {std::min(m.g2l[c[0]], std::min(m.g2l[c[1]], m.g2l[c[2]])), lc[k]};
-    }
+    parallel_for(m.ne, [&](int64_t a, int64_t b, int) {
+      for (int64_t k = a; k < b; ++k) {
+        const int32_t* c = cells + 3 * (int64_t)lc[k];
+        key[k] = {std::min(m.g2l[c[0]], std::min(m.g2l[c[1]], m.g2l[c[2]])), lc[k]};
+      }
+    });
     if (reorder) parallel_stable_sort(key.begin(), key.end(), [](const std::pair<int32_t, int32_t>& a, const std::pair<int32_t, int32_t>& b) { return a.first < b.first; });
     m.cell_l2g.resize(m.ne);
     m.cells.resize(3 * (size_t)m.ne);
-    for (int32_t k = 0; k < m.ne; ++k) {
-      m.cell_l2g[k] = key[k].second;
-      const int32_t* c = cells + 3 * (int64_t)key[k].second;
-      for (int i = 0; i < 3; ++i) m.cells[3 * (size_t)k + i] = m.g2l[c[i]];
-    }
+    parallel_for(m.ne, [&](int64_t a, int64_t b, int) {
+      for (int64_t k = a; k < b; ++k) {
+        m.cell_l2g[k] = key[k].second;
+        const int32_t* c = cells + 3 * (int64_t)key[k].second;
+        for (int i = 0; i < 3; ++i) m.cells[3 * (size_t)k + i] = m.g2l[c[i]];
+      }
+    });
   }
   m.x.resize(m.n_local);
   m.y.resize(m.n_local);
-  for (int32_t l = 0; l < m.n_local; ++l) { m.x[l] = xy[2 * (int64_t)m.l2g[l]]; m.y[l] = xy[2 * (int64_t)m.l2g[l] + 1]; }
+  parallel_for(m.n_local, [&](int64_t a, int64_t b, int) {
+    for (int64_t l = a; l < b; ++l) { m.x[l] = xy[2 * (int64_t)m.l2g[l]]; m.y[l] = xy[2 * (int64_t)m.l2g[l] + 1]; }
+  });
+  lap("maps, cell sort, coordinates");
   // CSR of owned rows
   const int32_t no = m.n_owned;
-  m.A = adjacency(no, m.n_local, m.ne, m.cells.data(), [no](int32_t v) { return v < no ? (int64_t)v : (int64_t)-1; });
   {
+    RawAdj adj = adjacency(no, m.n_local, m.ne, m.cells.data(), [no](int32_t v) { return v < no ? (int64_t)v : (int64_t)-1; });
     std::vector<int32_t> diag(no);
     std::iota(diag.begin(), diag.end(), 0);
-    finish_rows(m.A, diag);
+    finish_rows(adj, diag);
+    m.A = std::move(static_cast<HostCsr&>(adj));
   }
   m.S = sell_from_csr(m.A);
+  lap("CSR + SELL pattern");
   // slot table and diagonal positions
   m.slot.assign(9 * (size_t)m.ne, -1);
   auto find = [&](int32_t r, int32_t c) -> int32_t {
@@ -494,17 +561,27 @@ void build_host_mesh(int64_t nv, int64_t ne, const double* xy, const int32_t* ce
   parallel_for(no, [&](int64_t r0, int64_t r1, int) {
     for (int64_t r = r0; r < r1; ++r) m.diag_pos[r] = find((int32_t)r, (int32_t)r);
   });
+  lap("slot table + diagonal");
   // winning cell: highest caller cell id containing the vertex
+  // (caller cell id << 32 | local cell id), maximised per row with a compare-and-swap loop on all threads:
+  // caller ids are distinct, so the maximum -- and with it the result -- does not depend on the visiting order
   m.win_cell.assign(no, -1);
-  std::vector<int32_t> win_local(no, -1);
-  for (int32_t e = 0; e < m.ne; ++e)
-    for (int a = 0; a < 3; ++a) {
-      int32_t r = m.cells[3 * (size_t)e + a];
-      if (r < no && m.cell_l2g[e] > m.win_cell[r]) { m.win_cell[r] = m.cell_l2g[e]; win_local[r] = e; }
-    }
+  std::vector<int64_t> win_key(no, -1);
+  parallel_for(m.ne, [&](int64_t e0, int64_t e1, int) {
+    for (int64_t e = e0; e < e1; ++e)
+      for (int a = 0; a < 3; ++a) {
+        const int32_t r = m.cells[3 * (size_t)e + a];
+        if (r >= no) continue;
+        const int64_t k = ((int64_t)m.cell_l2g[e] << 32) | (int64_t)e;
+        int64_t cur = __atomic_load_n(&win_key[r], __ATOMIC_RELAXED);
+        while (k > cur && !__atomic_compare_exchange_n(&win_key[r], &cur, k, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+      }
+  });
   m.win.assign(4 * (size_t)no, 0);
-  for (int32_t r = 0; r < no; ++r) {
-    int32_t e = win_local[r];
+  parallel_for(no, [&](int64_t ra, int64_t rb, int) {
+  for (int64_t r = ra; r < rb; ++r) {
+    const int32_t e = win_key[r] < 0 ? -1 : (int32_t)(win_key[r] & 0xFFFFFFFFLL);
+    if (e >= 0) m.win_cell[r] = m.cell_l2g[e];
     if (e < 0) {  // isolated vertex: degenerate 'cell' of itself (gradients vanish)
       m.win[4 * (size_t)r] = m.win[4 * (size_t)r + 1] = m.win[4 * (size_t)r + 2] = r;
       m.win[4 * (size_t)r + 3] = -1;
@@ -517,6 +594,8 @@ void build_host_mesh(int64_t nv, int64_t ne, const double* xy, const int32_t* ce
     }
     m.win[4 * (size_t)r + 3] = loc;
   }
+  });
+  lap("winning cells");
   // halo maps
   m.nbrs.clear();
   if (nranks > 1) {
