@@ -253,3 +253,34 @@ def test_async_saver_places_owned_slices_and_double_buffers(monkeypatch):
         for k in range(4):
             assert np.array_equal(arrays[k][j], truth[j][k])
     assert saver.sets[0][0] is not saver.sets[1][0]
+
+
+def test_newton_solver_forwards_dolfinx_attributes():
+    """B200NewtonSolver mirrors the DOLFINx NewtonSolver attributes a user may set after pde_solver() returned
+    (reference solvers.py:52 leaves them at their defaults): rtol, atol, max_it and relaxation_parameter reach the
+    library's options before the next solve, and only when they changed.  Fake model, no GPU."""
+    import solvers
+    from types import SimpleNamespace
+
+    class FakeModel:
+        def __init__(self):
+            self.options = SimpleNamespace(newton_rtol=1e-9, newton_atol=1e-10, newton_max_it=50, newton_relaxation=1.0)
+            self.pushed = []
+
+        def set_options(self, **kw):
+            self.pushed.append(kw)
+            for k, v in kw.items():
+                setattr(self.options, k, v)
+
+        def newton_solve(self, dt):
+            return 3, True
+
+    s = solvers.B200NewtonSolver.__new__(solvers.B200NewtonSolver)
+    s.model, s.dt, s.sync_host = FakeModel(), SimpleNamespace(value=3600.0), False
+    assert s.solve(None) == (3, True) and s.model.pushed == []          # defaults: nothing to push
+    s.relaxation_parameter = 0.8
+    s.rtol = 1e-8
+    s.solve(None)
+    assert s.model.pushed == [dict(newton_rtol=1e-8, newton_atol=1e-10, newton_max_it=50, newton_relaxation=0.8)]
+    s.solve(None)
+    assert len(s.model.pushed) == 1                                      # unchanged: not pushed again
