@@ -244,3 +244,20 @@ def test_c_backend_is_the_same_restatement(c_backend, kw):
     for dt in (360.0, 3600.0, 3600.0):
         assert o1.step(dt)[0] == o2.step(dt)[0]
     assert relinf(o2.N, o1.N) < 1e-10 and relinf(o2.b, o1.b) < 1e-10 and relinf(o2.melt_n, o1.melt_n) < 1e-9
+
+
+def test_line_search_is_not_a_cure_on_the_negative_gap_start_state():
+    """Why newton_line_search is off by default ("Step length"): on the reference's hard start state
+    (setup_cooke2.py:66: gap height negative at ~40 % of the nodes) the plain Newton iteration of the reference wanders
+    -- the residual goes up and down -- and converges; forcing ||F||_2 to decrease monotonically stalls instead."""
+    c = make_case(seed=4, neg_b=True, turbulent=False)
+    o = make_oracle(*c)
+    it, conv = o.newton(360.0)
+    r = np.array(o.residual_history)
+    assert conv and it > 10 and np.any(r[2:] > r[1:-1])       # non-monotone, yet it converges
+    o = make_oracle(*c)
+    o.line_search = 6
+    with pytest.raises(RuntimeError):
+        o.newton(360.0)
+    r = np.array(o.residual_history)
+    assert o.backtracks > 0 and r[-1] > 1e-3 * r[1]            # stalled far from the root
