@@ -116,8 +116,12 @@ def _oracle_backend():
     fill-reducing MMD(A'+A) ordering for SuperLU; otherwise the numpy restatement.  Both are the same algorithm
     (tests/test_oracle.py: 1e-13)."""
     from oracle import cbackend
-    if cbackend.available():
-        return dict(backend="c", permc_spec="MMD_AT_PLUS_A"), cbackend.threads(), "C element kernels (OpenMP) + scipy SuperLU, MMD(A'+A) ordering"
+    try:
+        if cbackend.available():
+            return (dict(backend="c", permc_spec="MMD_AT_PLUS_A"), cbackend.threads(),
+                    "C element kernels (OpenMP) + scipy SuperLU, MMD(A'+A) ordering")
+    except OSError as e:                      # library built for another host: say so and time the numpy form
+        print(f"[bench] oracle C backend not loadable ({e}); CPU arm uses the numpy oracle", file=sys.stderr)
     return {}, cpu_threads(), "numpy element kernels + scipy SuperLU"
 
 
