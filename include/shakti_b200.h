@@ -140,7 +140,9 @@ int shakti_default_params(shakti_params* p);
  *   xy    : n_vert x 2 (row-major) vertex coordinates  (domain.geometry.x[:,0:2])
  *   cells : n_cell x 3 (row-major) vertex ids per triangle (V.dofmap.list == geometry dofmap)
  * For multi-GPU runs call shakti_comm_init first on every rank and pass the same GLOBAL mesh
- * on every rank; the library keeps the rank's partition. */
+ * on every rank; the library keeps the rank's partition.
+ * Every vertex must belong to at least one cell (DOLFINx drops unreferenced nodes when it builds a mesh):
+ * a mesh with such a vertex is refused with SHAKTI_ERR_INVALID on every rank. */
 int shakti_create(int64_t n_vert, int64_t n_cell, const double* xy, const int32_t* cells,
                   const shakti_params* params, const shakti_options* opt, int device,
                   shakti_model** out);

@@ -8,6 +8,7 @@
 #include <memory>
 #include <numeric>
 #include <stdexcept>
+#include <string>
 #include <thread>
 
 #include <chrono>
@@ -454,8 +455,21 @@ void build_host_mesh(int64_t nv, int64_t ne, const double* xy, const int32_t* ce
                      int nranks, int reorder, HostMesh& m) {
   if (nv <= 0 || ne <= 0) throw std::runtime_error("empty mesh");
   if (nv > 2000000000LL || ne > 2000000000LL / 3) throw std::runtime_error("mesh too large for int32 indices");
-  for (int64_t i = 0; i < 3 * ne; ++i)
-    if (cells[i] < 0 || cells[i] >= nv) throw std::runtime_error("cell vertex id out of range");
+  {
+    // Every rank validates the GLOBAL mesh, so that all ranks of a job fail together.  A vertex that belongs to no
+    // cell would be an empty Jacobian row (a singular system); DOLFINx never creates such a dof -- its mesh builder
+    // keeps only the nodes the cells refer to, and so does meshio_lite.read_msh_arrays -- so it is refused here
+    // with a message instead of producing NaNs in the first solve.
+    std::vector<uint8_t> used(nv, 0);
+    for (int64_t i = 0; i < 3 * ne; ++i) {
+      if (cells[i] < 0 || cells[i] >= nv) throw std::runtime_error("cell vertex id out of range");
+      used[cells[i]] = 1;
+    }
+    for (int64_t v = 0; v < nv; ++v)
+      if (!used[v])
+        throw std::runtime_error("vertex " + std::to_string(v) + " belongs to no cell: remove unreferenced nodes before "
+                                 "shakti_create (DOLFINx drops them when it builds the mesh)");
+  }
   m.nv_g = nv; m.ne_g = ne; m.rank = rank; m.nranks = nranks;
   g_host_thread_share = std::max(1, nranks);
   PrepLaps lap;

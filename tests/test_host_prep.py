@@ -247,3 +247,56 @@ def test_symmetric_heap_allocator_selftest():
         bad = C.c_int32(-1)
         assert lib.shakti_host_heap_selftest(C.c_int64(heap), C.c_int32(rounds), C.byref(bad)) == 0
         assert bad.value == 0, (heap, rounds, bad.value)
+
+
+def _rows_match_oracle(xy, cells, nranks):
+    nv = xy.shape[0]
+    rp, col = csr_pattern(nv, cells)
+    owned = []
+    for r in range(nranks):
+        hm = capi.HostMesh(xy, cells, r, nranks)
+        l2g, no = hm.array("l2g"), hm.n_owned
+        owned.append(l2g[:no])
+        rowptr, lcol = hm.array("rowptr"), hm.array("col")
+        for i in range(no):
+            assert np.array_equal(np.sort(l2g[lcol[rowptr[i]:rowptr[i + 1]]]), col[rp[l2g[i]]:rp[l2g[i] + 1]])
+        hm.array("ab_eptr")                      # the assembly plan builds (or reports the atomic fallback)
+    assert np.array_equal(np.sort(np.concatenate(owned)), np.arange(nv))     # ownership is a partition
+
+
+@pytest.mark.parametrize("kind", ["holes", "duplicated-cell", "tiny"])
+def test_odd_meshes_preprocess_consistently(kind):
+    """Ragged inputs: meshes with holes (dropped cells, unreferenced nodes pruned as DOLFINx does), a duplicated cell
+    (three cells on an edge: the row-block plan must step aside, not miscount) and meshes with fewer rows than a
+    SELL slice / than ranks -- every owned row's pattern equals the oracle's on 1, 2 and 3 ranks."""
+    rng = np.random.default_rng(5)
+    for trial in range(8):
+        nx, ny = (int(rng.integers(1, 3)), int(rng.integers(1, 3))) if kind == "tiny" else (int(rng.integers(2, 9)), int(rng.integers(2, 9)))
+        xy, cells = meshgen.rectangle(nx, ny, 1.0, 1.0, jitter=0.2, seed=trial, diagonal="random")
+        xy, cells = meshgen.scramble(xy, cells, seed=trial)
+        if kind == "holes":
+            keep = rng.random(cells.shape[0]) > 0.4
+            keep[0] = True
+            cells = cells[keep]
+            used = np.zeros(xy.shape[0], bool)
+            used[cells.ravel()] = True
+            cells = np.ascontiguousarray((np.cumsum(used) - 1)[cells], dtype=np.int32)
+            xy = np.ascontiguousarray(xy[used])
+        if kind == "duplicated-cell":
+            cells = np.ascontiguousarray(np.vstack([cells, cells[:1]]))
+        for nranks in (1, 2, 3):
+            if nranks <= xy.shape[0]:
+                _rows_match_oracle(xy, cells, nranks)
+
+
+def test_unreferenced_vertex_is_refused():
+    """A node no cell refers to would be an empty Jacobian row (singular system).  DOLFINx never creates such a dof;
+    the library refuses the mesh with a message naming the vertex (and the .msh reader prunes such nodes)."""
+    xy, cells = meshgen.rectangle(3, 3, 1.0, 1.0)
+    xy2 = np.vstack([xy, [[9.0, 9.0]]])
+    with pytest.raises(capi.ShaktiError) as e:
+        capi.HostMesh(xy2, cells)
+    assert "vertex 16 belongs to no cell" in str(e.value)
+    for rank in (0, 1):                          # every rank of a job refuses it (no rank is left waiting)
+        with pytest.raises(capi.ShaktiError):
+            capi.HostMesh(xy2, cells, rank, 2)
