@@ -1436,10 +1436,18 @@ struct shakti_host_mesh {
   bool ab_built = false;
 };
 
+// the host-only entry points take caller data that no shakti_create has looked at yet
+static void require_valid_cells(int64_t n_vert, int64_t n_cell, const int32_t* cells) {
+  SHAKTI_REQUIRE(n_vert > 0 && n_cell > 0 && n_vert <= 2000000000LL && n_cell <= 2000000000LL / 3, "mesh size out of range");
+  for (int64_t i = 0; i < 3 * n_cell; ++i)
+    SHAKTI_REQUIRE(cells[i] >= 0 && cells[i] < n_vert, "cell vertex id out of range");
+}
+
 int shakti_host_csr_pattern(int64_t n_vert, int64_t n_cell, const int32_t* cells, int32_t* rowptr, int32_t* col,
                             int64_t* nnz) {
   SHAKTI_TRY
   SHAKTI_REQUIRE(cells && nnz && n_vert > 0 && n_cell > 0, "bad arguments");
+  require_valid_cells(n_vert, n_cell, cells);
   HostCsr a = caller_csr(n_vert, n_cell, cells);
   *nnz = a.nnz();
   if (rowptr) std::copy(a.rowptr.begin(), a.rowptr.end(), rowptr);
@@ -1450,6 +1458,7 @@ int shakti_host_locate_dirichlet(int64_t n_vert, int64_t n_cell, const int32_t* 
                                  int32_t* dofs, int64_t cap, int64_t* n_out) {
   SHAKTI_TRY
   SHAKTI_REQUIRE(cells && marker && n_out, "null argument");
+  require_valid_cells(n_vert, n_cell, cells);
   std::vector<int32_t> d = locate_dirichlet_dofs(n_vert, n_cell, cells, marker);
   *n_out = (int64_t)d.size();
   if (dofs) {

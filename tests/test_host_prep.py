@@ -300,3 +300,19 @@ def test_unreferenced_vertex_is_refused():
     for rank in (0, 1):                          # every rank of a job refuses it (no rank is left waiting)
         with pytest.raises(capi.ShaktiError):
             capi.HostMesh(xy2, cells, rank, 2)
+
+
+def test_host_entry_points_validate_cell_ids():
+    """Caller data reaches the host-only entry points unchecked by any shakti_create: a vertex id outside
+    [0, n_vert) must come back as an error, not as a write outside the arrays."""
+    xy, cells = meshgen.rectangle(3, 3, 1.0, 1.0)
+    nv = xy.shape[0]
+    for bad_id in (nv, -1, 2**31 - 1):
+        bad = cells.copy()
+        bad[4, 1] = bad_id
+        with pytest.raises(capi.ShaktiError):
+            capi.host_csr_pattern(nv, bad)
+        with pytest.raises(capi.ShaktiError):
+            capi.host_locate_dirichlet(nv, bad, np.ones(nv, bool))
+        with pytest.raises(capi.ShaktiError):
+            capi.HostMesh(xy, bad)
