@@ -469,6 +469,19 @@ void build_host_mesh(int64_t nv, int64_t ne, const double* xy, const int32_t* ce
       if (!used[v])
         throw std::runtime_error("vertex " + std::to_string(v) + " belongs to no cell: remove unreferenced nodes before "
                                  "shakti_create (DOLFINx drops them when it builds the mesh)");
+    // non-finite coordinates or a cell of zero area make 1/det J infinite in every kernel: name the cell instead
+    int64_t bad_cell = -1;
+    parallel_for(ne, [&](int64_t e0, int64_t e1, int) {
+      for (int64_t e = e0; e < e1; ++e) {
+        const int32_t* c = cells + 3 * e;
+        const double d1x = xy[2 * (int64_t)c[1]] - xy[2 * (int64_t)c[0]], d1y = xy[2 * (int64_t)c[1] + 1] - xy[2 * (int64_t)c[0] + 1];
+        const double d2x = xy[2 * (int64_t)c[2]] - xy[2 * (int64_t)c[0]], d2y = xy[2 * (int64_t)c[2] + 1] - xy[2 * (int64_t)c[0] + 1];
+        const double det = d1x * d2y - d2x * d1y;
+        if (!(std::fabs(det) > 0.0) || !std::isfinite(det)) __atomic_store_n(&bad_cell, e, __ATOMIC_RELAXED);
+      }
+    });
+    if (bad_cell >= 0)
+      throw std::runtime_error("cell " + std::to_string(bad_cell) + " has zero area or non-finite vertex coordinates");
   }
   m.nv_g = nv; m.ne_g = ne; m.rank = rank; m.nranks = nranks;
   g_host_thread_share = std::max(1, nranks);

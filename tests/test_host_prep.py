@@ -316,3 +316,20 @@ def test_host_entry_points_validate_cell_ids():
             capi.host_locate_dirichlet(nv, bad, np.ones(nv, bool))
         with pytest.raises(capi.ShaktiError):
             capi.HostMesh(xy, bad)
+
+
+def test_degenerate_geometry_is_refused():
+    """A cell of zero area (or a NaN coordinate) makes 1/det J infinite in every kernel; the mesh is refused with the
+    cell named (the reference would carry NaNs into its first Newton solve)."""
+    xy, cells = meshgen.rectangle(3, 3, 1.0, 1.0)
+    flat = xy.copy()
+    c = cells[5]
+    flat[c[2]] = flat[c[0]]                                # two vertices of a cell coincide: zero area
+    with pytest.raises(capi.ShaktiError) as e:
+        capi.HostMesh(flat, cells)
+    assert "zero area" in str(e.value)
+    nan = xy.copy()
+    nan[7, 0] = np.nan
+    with pytest.raises(capi.ShaktiError):
+        capi.HostMesh(nan, cells)
+    capi.HostMesh(xy, cells)                               # the undisturbed mesh is fine
