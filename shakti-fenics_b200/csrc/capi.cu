@@ -419,6 +419,7 @@ static void newton_solve(shakti_model* m, double dt, int32_t* niter, int32_t* co
       // The iteration converged one step earlier than the model expected, i.e. after a LOOSE solve.  The
       // iterate must not depend on that: one more correction with the current Jacobian, solved tightly
       // (not counted as a Newton iteration -- the exact iteration would have stopped here too).
+      if (!have_J) assemble(m, dt, 1);   // only after a backtracked step: the trial residuals were F-only
       launch_xmy_masked(no, m->F.p, m->isbc.p, m->rhs.p, m->stream);
       m->newton_it_in_step = it;
       KrylovResult kp = linear_solve(m, m->rhs.p, m->dx.p, std::min(1e-2, r > 0 ? tau_tight / r : 1e-2));
