@@ -234,6 +234,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun gives every rank OMP_NUM_THREADS=1; here the other ranks have just exited, so rank 0 may use the
+    # whole host (the OpenMP runtime of the oracle's C kernels reads the variable when the library is loaded, below)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and os.environ.get("OMP_NUM_THREADS") == "1":
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     nside = args.nside or 4000
     target = nside * nside
     nside_cpu = cpu_sample_nside(args.cpu_sample_nside, args.steps + 1)
